@@ -19,7 +19,7 @@ typedef struct {
     int64_t counts[4];
 } sink_t;
 
-static void emit(sink_t *s, int stream, int start, int end, int mlen) {
+static void emit(sink_t *s, int stream, int start, int end, int mlen, int time) {
     s->counts[stream]++;
     if (s->count_only) { s->n++; return; }
     if (s->n == s->cap) {
@@ -29,6 +29,7 @@ static void emit(sink_t *s, int stream, int start, int end, int mlen) {
         s->v = nv; s->cap = nc;
     }
     s->v[s->n].stream = stream; s->v[s->n].start = start; s->v[s->n].end = end; s->v[s->n].mlen = mlen;
+    s->v[s->n].time = time;
     s->n++;
 }
 
@@ -63,7 +64,7 @@ static void scan_perfect(const uint8_t *code, const uint8_t *nn, int64_t L, int 
                 int m = m_lo + d, midx = m - s_lo;
                 int cutoff = (m <= 6) ? 12 - m : m + midx; /* :179 */
                 if (last[d] != -1) {
-                    if ((int)p - last[d] >= cutoff) emit(out, 1, last[d], (int)p, m);
+                    if ((int)p - last[d] >= cutoff) emit(out, 1, last[d], (int)p, m, (int)p);
                     last[d] = -1;
                 }
             }
@@ -74,7 +75,7 @@ static void scan_perfect(const uint8_t *code, const uint8_t *nn, int64_t L, int 
                 if (X(code, L, m, p)) {
                     if (last[d] == -1) last[d] = (int)p;
                 } else {
-                    if (last[d] != -1 && (int)p - last[d] >= cutoff) emit(out, 1, last[d], (int)p, m);
+                    if (last[d] != -1 && (int)p - last[d] >= cutoff) emit(out, 1, last[d], (int)p, m, (int)p);
                     last[d] = -1;
                 }
             }
@@ -85,7 +86,7 @@ static void scan_perfect(const uint8_t *code, const uint8_t *nn, int64_t L, int 
         int m = m_lo + d;
         int cutoff = (m <= 6) ? 12 - m : m;
         if (last[d] != -1) {
-            if (wp - last[d] >= cutoff) emit(out, 1, last[d], wp, m);
+            if (wp - last[d] >= cutoff) emit(out, 1, last[d], wp, m, -1);
             last[d] = -1;
         }
     }
@@ -147,7 +148,7 @@ static void scan_windows(const yctx_t *c, const uint8_t *nn, int m_lo, int m_hi,
                 if (cur[d] != -1) {
                     cur[d] = wp;
                     if (le[d] != -1 && le[d] < cur[d]) {
-                        emit(out, stream, ls[d], le[d], m_lo + d);
+                        emit(out, stream, ls[d], le[d], m_lo + d, (int)p);
                         ls[d] = -1; le[d] = -1;
                     }
                 }
@@ -165,7 +166,7 @@ static void scan_windows(const yctx_t *c, const uint8_t *nn, int m_lo, int m_hi,
                         if (cur[d] == -1) {
                             cur[d] = wp;
                             if (le[d] != -1 && le[d] < cur[d]) {
-                                emit(out, stream, ls[d], le[d], m);
+                                emit(out, stream, ls[d], le[d], m, (int)p);
                                 ls[d] = -1; le[d] = -1;
                             }
                         }
@@ -175,7 +176,7 @@ static void scan_windows(const yctx_t *c, const uint8_t *nn, int m_lo, int m_hi,
                             else le[d] = wp + 8 - 1;
                             cur[d] = -1;
                         } else if (le[d] != -1 && le[d] < wp) {
-                            emit(out, stream, ls[d], le[d], m);
+                            emit(out, stream, ls[d], le[d], m, (int)p);
                             ls[d] = -1; le[d] = -1;
                         }
                     }
@@ -187,14 +188,14 @@ static void scan_windows(const yctx_t *c, const uint8_t *nn, int m_lo, int m_hi,
     for (int d = 0; d < nm; d++) {
         int m = m_lo + d;
         if (le[d] == -1) {
-            if (cur[d] != -1) emit(out, stream, cur[d], (int)L, m);
+            if (cur[d] != -1) emit(out, stream, cur[d], (int)L, m, -1);
         } else if (cur[d] == -1) {
-            emit(out, stream, ls[d], le[d], m);
+            emit(out, stream, ls[d], le[d], m, -1);
         } else if (le[d] >= cur[d] - m) {
-            emit(out, stream, ls[d], (int)L, m);
+            emit(out, stream, ls[d], (int)L, m, -1);
         } else {
-            emit(out, stream, ls[d], le[d], m);
-            emit(out, stream, cur[d], (int)L, m);
+            emit(out, stream, ls[d], le[d], m, -1);
+            emit(out, stream, cur[d], (int)L, m, -1);
         }
     }
     free(ls);

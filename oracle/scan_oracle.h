@@ -25,6 +25,7 @@ typedef struct {
     int32_t start;
     int32_t end;
     int32_t mlen;
+    int32_t time; /* position being processed when the reference makes the call; -1 = tail flush after the loop */
 } rbo_event;
 
 /* Scans one contig (ASCII, length L) for motif sizes [min_mlen, max_mlen].

@@ -1,0 +1,515 @@
+// ribbit-b200: per-lane scan logic shared by the sm_100a kernels (scan_kernels.cu) and by the CPU warp
+// emulator that tests/ uses to check the kernel logic without a GPU (tests/emu/emu_scan.cpp).
+//
+// Mapping: one warp lane owns one shift s of one band; a lane whose shift is a motif size m
+// of the band additionally runs the three seed machines of the reference for that m:
+//   perfect   parse_perfect_shiftxor.cpp:146-226      (runs of X_m & ~N)
+//   subst     parse_substitute_shiftxor.cpp:391-577   (8-window, >=7 matches, Y = X_m)
+//   anchored  parse_anchored_shiftxor.cpp:538-726     (8-window, >=6 matches, Y = B_m)
+// with  X_s  fasta_utils.cpp:117-122,  anchors A_s  parse_anchored_shiftxor.cpp:20-56,
+//       B_m  fasta_utils.cpp:143-161.
+// A lane walks the words (32 positions each) of its chunk in order. Words whose eight-position windows are all
+// valid ("fast" words: no N within [32w-7, 32w+31], inside the contig) are handled bit-parallel; every other word
+// ("slow" word) is handled bit-serially with the reference's state machine verbatim.
+#ifndef RB_SCAN_CORE_H
+#define RB_SCAN_CORE_H
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define RB_HD __host__ __device__ __forceinline__
+#else
+#define RB_HD inline
+#endif
+
+namespace rb {
+
+// One word of the packed contig: 32 positions, bit i = position 32*w + i.
+//  h, l : high / low bit of the 2-bit base code (A=00 C=01 G=10 T=11; N and padding 00)   fasta_utils.cpp:95-113
+//  n    : N plane (anything that is not ACGTacgt); padding past the contig end is 1
+//  v    : window-valid plane: v[p] = 1 iff p >= 7, p < L and no N in [p-7, p]  (the reference's
+//         `valid_position >= window_length` test, parse_substitute_shiftxor.cpp:469)
+struct PlaneWord {
+    uint32_t h, l, n, v;
+};
+
+enum : int {
+    STREAM_P = 0,
+    STREAM_S = 1,
+    STREAM_A = 2,
+};
+enum : int {
+    REC_DROPPED = 1,   // below the consumer's length cutoff: only advances the consumer's cursors
+    REC_PSEUDO = 2,    // synthetic cursor-advance record (end = max end of elided dropped candidates)
+    REC_NOCOMMIT = 4,  // anchored tail flush whose returned cursors the reference discards
+};
+static const int LEN_SAT = 1 << 24;
+
+struct Rec {
+    int32_t start, end;
+    int32_t mflags;  // mlen | flags << 16
+    int32_t key;     // (time - 32*bucket) << 18 | mlen << 2 | seq   (order inside a bucket)
+};
+
+RB_HD int ctz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return x ? __ffs((int)x) - 1 : 32;
+#else
+    return x ? __builtin_ctz(x) : 32;
+#endif
+}
+RB_HD int clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+// low 32 bits of (hi:lo) >> k, 0 <= k < 32
+RB_HD uint32_t fsr(uint32_t lo, uint32_t hi, int k) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, k);
+#else
+    return k ? (lo >> k) | (hi << (32 - k)) : lo;
+#endif
+}
+// high 32 bits of (hi:lo) << k, 0 <= k < 32: value[p] = in[p-k] with `lo` the previous word
+RB_HD uint32_t fsl(uint32_t lo, uint32_t hi, int k) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, k);
+#else
+    return k ? (hi << k) | (lo >> (32 - k)) : hi;
+#endif
+}
+RB_HD uint32_t lowmask(int nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
+
+struct LaneCfg {
+    int s;       // shift handled by this lane (>= 1), 0 = idle lane
+    int motif;   // 1 if the lane runs the seed machines for m = s
+    int cutP;    // perfect cutoff, run closed by a mismatch or the contig end   parse_perfect_shiftxor.cpp:193,216
+    int cutPN;   // perfect cutoff, run closed by an N                            parse_perfect_shiftxor.cpp:179
+    int cutS;    // substitution keep cutoff  (m>30 ? m/3 : 10)                   parse_substitute_shiftxor.cpp:423
+    int cutA;    // anchored keep cutoff                                          parse_anchored_shiftxor.cpp:572-573
+};
+
+RB_HD LaneCfg make_lane_cfg(int s, int m_lo, int m_hi, int s_lo, int s_hi, int band_m0, int band_m1) {
+    LaneCfg c;
+    c.s = (s >= s_lo && s <= s_hi && s >= 1) ? s : 0;
+    c.motif = (c.s != 0 && s >= m_lo && s <= m_hi && s >= band_m0 && s <= band_m1) ? 1 : 0;
+    c.cutP = (s <= 6) ? 12 - s : s;
+    c.cutPN = (s <= 6) ? 12 - s : s + (s - s_lo);
+    c.cutS = (s > 30) ? s / 3 : 10;
+    c.cutA = (s > 6) ? s : 10;
+    if (s >= 10) c.cutA = (int)(0.9 * s);
+    return c;
+}
+
+// X_s word: bit p set iff code[p] == code[p+s] (zeros are shifted in past the contig end because the padding
+// words are zero)  fasta_utils.cpp:121.  `cw` points at word 0 of the contig; indices -1 .. nw+guard-1 are readable.
+RB_HD uint32_t x_word(const PlaneWord* cw, int w, int s) {
+    const int off = s >> 5, sh = s & 31;
+    const PlaneWord o = cw[w], a = cw[w + off], b = cw[w + off + 1];
+    const uint32_t th = o.h ^ fsr(a.h, b.h, sh);
+    const uint32_t tl = o.l ^ fsr(a.l, b.l, sh);
+    return ~(th | tl);
+}
+
+// positions p >= L - s never close an anchor run (parse_anchored_shiftxor.cpp:37): force them to 1 so that the
+// run that reaches L-1-s looks unbounded and is dropped by the "< 2*s" test.
+RB_HD uint32_t anchor_endmask(int w, int L, int s) {
+    const long long lim = (long long)L - s - 32ll * w;  // first masked bit index in this word
+    if (lim >= 32) return 0u;
+    if (lim <= 0) return 0xFFFFFFFFu;
+    return 0xFFFFFFFFu << lim;
+}
+
+// number of consecutive 1s of the anchor view of X_s starting at bit 0 of word w, capped at `cap`
+RB_HD int anchor_ones_from(const PlaneWord* cw, int w, int L, int s, int cap) {
+    int tot = 0;
+    while (tot < cap) {
+        if (32ll * w >= (long long)L - s) return cap;  // everything from here on is forced to 1
+        const uint32_t xa = x_word(cw, w, s) | anchor_endmask(w, L, s);
+        const int k = ctz32(~xa);
+        tot += k;
+        if (k < 32) break;
+        ++w;
+    }
+    return tot < cap ? tot : cap;
+}
+
+// Anchor word A_s[w] (parse_anchored_shiftxor.cpp:34-55): runs of 1s of X_s with 3 <= len < 2s that are closed
+// inside the scanned range. lenL = length of the run of 1s ending at bit 31 of word w-1 (saturating).
+RB_HD uint32_t anchor_word(const PlaneWord* cw, int w, int L, int s, uint32_t xa, uint32_t xa_nxt, int& lenL) {
+    const int K2 = 2 * s;
+    if (xa == 0u) { lenL = 0; return 0u; }
+    const int lead = ctz32(~xa);
+    if (lead == 32) {  // the whole word is inside one run
+        uint32_t a = 0u;
+        if (lenL + 32 < K2) {
+            int rext = ctz32(~xa_nxt);
+            if (rext == 32) rext = 32 + anchor_ones_from(cw, w + 2, L, s, K2);
+            if (lenL + 32 + rext < K2) a = 0xFFFFFFFFu;
+        }
+        lenL = (lenL + 32 > LEN_SAT) ? LEN_SAT : lenL + 32;
+        return a;
+    }
+    const int trail = clz32(~xa);
+    uint32_t a = 0u, mid = xa;
+    if (lead > 0) {
+        const int tot = lenL + lead;
+        if (tot >= 3 && tot < K2) a |= lowmask(lead);
+        mid &= ~lowmask(lead);
+    }
+    if (trail > 0) {
+        int rext = ctz32(~xa_nxt);
+        if (rext == 32 && trail + 32 < K2) rext = 32 + anchor_ones_from(cw, w + 2, L, s, K2);
+        const int tot = trail + rext;
+        if (tot >= 3 && tot < K2) a |= ~lowmask(32 - trail);
+        mid &= lowmask(32 - trail);
+    }
+    // runs strictly inside the word
+    const uint32_t r3 = mid & (mid >> 1) & (mid >> 2);
+    uint32_t keep = r3 | (r3 << 1) | (r3 << 2);
+    if (K2 <= 30 && keep) {
+        uint32_t e = mid;
+        for (int k = 1; k < K2;) { const int st = (k < K2 - k) ? k : K2 - k; e &= e >> st; k += st; }
+        if (e) {
+            uint32_t d = e;
+            for (int k = 1; k < K2;) { const int st = (k < K2 - k) ? k : K2 - k; d |= d << st; k += st; }
+            keep &= ~d;
+        }
+    }
+    lenL = trail;
+    return a | keep;
+}
+
+// carries of the bit-sliced "number of mismatches in the last 8 positions" counters (previous word)
+struct WinCarry {
+    uint32_t z, o1, t1, o2, t2, u2;
+};
+
+// fail mask for ">= 7 of 8" (substitution pass): bit p set iff Y[p-7..p] holds >= 2 zeros
+RB_HD uint32_t fail_ge2(uint32_t y, WinCarry& c) {
+    const uint32_t z = ~y;
+    const uint32_t z1 = fsl(c.z, z, 1);
+    const uint32_t o1 = z | z1, t1 = z & z1;
+    const uint32_t o1s = fsl(c.o1, o1, 2), t1s = fsl(c.t1, t1, 2);
+    const uint32_t o2 = o1 | o1s;
+    const uint32_t t2 = t1 | t1s | (o1 & o1s);
+    const uint32_t o2s = fsl(c.o2, o2, 4), t2s = fsl(c.t2, t2, 4);
+    const uint32_t t3 = t2 | t2s | (o2 & o2s);
+    c.z = z; c.o1 = o1; c.t1 = t1; c.o2 = o2; c.t2 = t2;
+    return t3;
+}
+// fail mask for ">= 6 of 8" (anchored pass): bit p set iff Y[p-7..p] holds >= 3 zeros
+RB_HD uint32_t fail_ge3(uint32_t y, WinCarry& c) {
+    const uint32_t z = ~y;
+    const uint32_t z1 = fsl(c.z, z, 1);
+    const uint32_t o1 = z | z1, t1 = z & z1;
+    const uint32_t o1s = fsl(c.o1, o1, 2), t1s = fsl(c.t1, t1, 2);
+    const uint32_t o2 = o1 | o1s;
+    const uint32_t t2 = t1 | t1s | (o1 & o1s);
+    const uint32_t u2 = (t1 & o1s) | (o1 & t1s);
+    const uint32_t o2s = fsl(c.o2, o2, 4), t2s = fsl(c.t2, t2, 4), u2s = fsl(c.u2, u2, 4);
+    const uint32_t u3 = u2 | u2s | (t2 & o2s) | (o2 & t2s);
+    c.z = z; c.o1 = o1; c.t1 = t1; c.o2 = o2; c.t2 = t2; c.u2 = u2;
+    return u3;
+}
+
+// reference window machine state for one motif and one stream (parse_substitute_shiftxor.cpp:408-410)
+struct WinState {
+    int cur, ls, le;
+};
+
+struct LaneState {
+    uint32_t x_prev, x_cur, x_nxt;  // X_s of words w-1, w, w+1
+    uint32_t b_prev;                // B_m of word w-1
+    int lenL;                       // anchor-view run length ending at the end of word w-1
+    WinCarry cs, ca;
+    int pst;                        // perfect machine: start of the open run or -1 (last_starts)
+    WinState S, A;
+    // warm-up bookkeeping (chunks that do not start at the contig start)
+    int sync;                       // bit0 anchors exact, bit1 perfect, bit2 subst, bit3 anchored
+    int zS, zA;                     // consecutive evaluated failing windows (saturating)
+};
+enum : int { SYNC_X = 1, SYNC_P = 2, SYNC_S = 4, SYNC_A = 8, SYNC_ALL = 15 };
+
+// Context of one lane iteration; the Sink receives the events.
+//   Sink::rec(stream, start, end, mlen, flags, key)   a record that goes to bucket `w` of the stream
+//   Sink::dropped(stream, tw)                          a fast-word candidate below the cutoff (only its time counts)
+struct IterCtx {
+    int w;        // word (bucket) being processed
+    int L;        // contig length
+    int emit_on;  // 0 while warming up (w < first owned word)
+    int slow;     // 1 if this word goes through the bit-serial path
+};
+
+template <class Sink>
+RB_HD void emit_win(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, int ls, int le, int time) {
+    if (!it.emit_on) return;
+    const int cut = (stream == STREAM_S) ? cfg.cutS : cfg.cutA;
+    const int tw = time - 32 * it.w;
+    if (le - ls >= cut) sk.rec(stream, ls, le, cfg.s, 0, (tw << 18) | (cfg.s << 2));
+    else if (it.slow) sk.rec(stream, ls, le, cfg.s, REC_DROPPED, (tw << 18) | (cfg.s << 2));
+    else sk.dropped(stream, tw);
+}
+template <class Sink>
+RB_HD void emit_perfect(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int start, int end, int time) {
+    if (!it.emit_on) return;
+    sk.rec(STREAM_P, start, end, cfg.s, 0, ((time - 32 * it.w) << 18) | (cfg.s << 2));
+}
+
+// ---- fast word: all 32 windows ending in this word are evaluated -------------------------------------------------
+// P bit i = window ending at position 32w+i (window start wp = 32w-7+i) passes.
+template <class Sink>
+RB_HD void win_fast(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, uint32_t P, WinState& st) {
+    if (P == 0u && st.cur < 0 && st.le < 0) return;
+    const int base = 32 * it.w - 7;
+    int i = 0;
+    if (st.cur >= 0) {
+        const int ones = ctz32(~P);
+        if (ones >= 32) return;  // the open run covers the whole word
+        if (st.ls < 0) st.ls = st.cur;
+        st.le = base + ones + 7;
+        st.cur = -1;
+        i = ones + 1;
+    }
+    for (;;) {
+        const uint32_t rest = (i < 32) ? (P >> i) : 0u;
+        const int a = rest ? i + ctz32(rest) : 32;
+        if (st.le >= 0) {
+            int e = st.le + 1 - base;  // first window start beyond the last component end
+            if (e < i) e = i;
+            if (a >= e) {
+                if (e >= 32) return;  // emitted by a later word
+                emit_win(sk, it, cfg, stream, st.ls, st.le, base + e + 7);
+                st.ls = -1; st.le = -1;
+            }
+        }
+        if (a >= 32) return;
+        st.cur = base + a;
+        const int ones = ctz32(~(P >> a));
+        if (a + ones >= 32) return;  // run still open at the end of the word
+        const int f = a + ones;
+        if (st.ls < 0) st.ls = st.cur;
+        st.le = base + f + 7;
+        st.cur = -1;
+        i = f + 1;
+    }
+}
+
+template <class Sink>
+RB_HD void perfect_fast(Sink& sk, const IterCtx& it, const LaneCfg& cfg, uint32_t g, int& pst) {
+    uint32_t r = g;
+    const int p0 = 32 * it.w;
+    if (pst >= 0) {
+        const int lead = ctz32(~r);
+        if (lead >= 32) return;
+        const int end = p0 + lead;
+        if (end - pst >= cfg.cutP) emit_perfect(sk, it, cfg, pst, end, end);
+        pst = -1;
+        r &= ~lowmask(lead);
+    }
+    const int trail = clz32(~r);
+    if (trail > 0) {
+        pst = p0 + 32 - trail;
+        r &= lowmask(32 - trail);
+    }
+    if (cfg.cutP > 30 || r == 0u) return;
+    const uint32_t e2 = r & (r >> 1), e4 = e2 & (e2 >> 2);
+    const uint32_t pre = (cfg.cutP >= 8) ? (e4 & (e4 >> 4)) : (e4 & (e2 >> 4));  // runs >= 8 / >= 6
+    if (pre == 0u) return;
+    while (r) {  // rare: some interior run may reach the cutoff
+        const int a = ctz32(r);
+        const int len = ctz32(~(r >> a));
+        if (len >= cfg.cutP) emit_perfect(sk, it, cfg, p0 + a, p0 + a + len, p0 + a + len);
+        r &= ~(lowmask(len) << a);
+    }
+}
+
+// ---- slow word: the reference state machines bit by bit ----------------------------------------------------------
+template <class Sink>
+RB_HD void win_slow_bit(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, int p, int nbit, int vbit, int pass,
+                        WinState& st, int& zrun, int& sync, int syncbit, int prev_v) {
+    const int wp = p - 7;
+    if (nbit) {  // parse_substitute_shiftxor.cpp:433-458
+        if (st.cur != -1) {
+            st.cur = wp;
+            if (st.le != -1 && st.le < st.cur) {
+                emit_win(sk, it, cfg, stream, st.ls, st.le, p);
+                st.ls = -1; st.le = -1;
+            }
+        }
+        st.cur = -1;
+        zrun = 0;
+    } else if (vbit) {  // :469-530
+        if (pass) {
+            if (st.cur == -1) {
+                st.cur = wp;
+                if (st.le != -1 && st.le < st.cur) {
+                    emit_win(sk, it, cfg, stream, st.ls, st.le, p);
+                    st.ls = -1; st.le = -1;
+                }
+            }
+            zrun = 0;
+        } else {
+            if (st.cur != -1) {
+                if (st.ls == -1) st.ls = st.cur;
+                st.le = wp + 7;
+                st.cur = -1;
+            } else if (st.le != -1 && st.le < wp) {
+                emit_win(sk, it, cfg, stream, st.ls, st.le, p);
+                st.ls = -1; st.le = -1;
+            }
+            if (zrun < 64) zrun++;
+        }
+        // warm-up: the state is history-free after the first window of a valid stretch or after 9 failing windows
+        if (!prev_v || zrun >= 9) sync |= syncbit;
+    } else {
+        zrun = 0;
+    }
+}
+
+// Tail flush of one stream after the last position (parse_substitute_shiftxor.cpp:534-574,
+// parse_anchored_shiftxor.cpp:681-723). Records go to the bucket after the last word; order key = (mlen, seq).
+template <class Sink>
+RB_HD void win_tail(Sink& sk, const LaneCfg& cfg, int stream, int L, const WinState& st) {
+    const int cut = (stream == STREAM_S) ? cfg.cutS : cfg.cutA;
+    const int m = cfg.s;
+    int s0 = -1, e0 = 0, s1 = -1, e1 = 0, commit0 = 1;
+    if (st.le == -1) {
+        if (st.cur != -1) { s0 = st.cur; e0 = L; commit0 = 0; }
+    } else if (st.cur == -1) {
+        s0 = st.ls; e0 = st.le; commit0 = 0;
+    } else if (st.le >= st.cur - m) {
+        s0 = st.ls; e0 = L; commit0 = 0;
+    } else {
+        s0 = st.ls; e0 = st.le; commit0 = 1;
+        s1 = st.cur; e1 = L;
+    }
+    // the substitution pass always stores the returned cursor; the anchored pass only for the first of two calls
+    const int nc0 = (stream == STREAM_A && !commit0) ? REC_NOCOMMIT : 0;
+    const int nc1 = (stream == STREAM_A) ? REC_NOCOMMIT : 0;
+    if (s0 != -1) {
+        if (e0 - s0 >= cut) sk.rec(stream, s0, e0, m, nc0, (m << 2) | 0);
+        else if (!nc0) sk.rec(stream, s0, e0, m, REC_DROPPED, (m << 2) | 0);
+    }
+    if (s1 != -1) {
+        if (e1 - s1 >= cut) sk.rec(stream, s1, e1, m, nc1, (m << 2) | 1);
+        else if (!nc1) sk.rec(stream, s1, e1, m, REC_DROPPED, (m << 2) | 1);
+    }
+}
+
+// ---- one lane, one word ------------------------------------------------------------------------------------------
+// Phase 1: bring X_s[w+1] in and compute the anchor word A_s[w]. Returns A_s[w] (0 for idle lanes).
+RB_HD uint32_t lane_phase1(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
+    if (cfg.s == 0) return 0u;
+    st.x_nxt = x_word(cw, w + 1, cfg.s);
+    const uint32_t xa = st.x_cur | anchor_endmask(w, L, cfg.s);
+    const uint32_t xan = st.x_nxt | anchor_endmask(w + 1, L, cfg.s);
+    if (xa != 0xFFFFFFFFu) st.sync |= SYNC_X;  // a zero was seen: run lengths are exact from here on
+    return anchor_word(cw, w, L, cfg.s, xa, xan, st.lenL);
+}
+
+// Phase 2: B_m[w] from the neighbouring anchors, window tests, seed machines, state rotation.
+template <class Sink>
+RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, const IterCtx& it,
+                       uint32_t a_m2, uint32_t a_m1, uint32_t a_p1, uint32_t a_p2, int machines_on) {
+    if (cfg.motif) {
+        const PlaneWord o = cw[it.w];
+        const uint32_t x = st.x_cur;
+        const uint32_t b = x | a_m2 | a_m1 | a_p1 | a_p2;
+        const uint32_t prev_v31 = cw[it.w - 1].v >> 31;
+        const uint32_t passS = ~fail_ge2(x, st.cs) & o.v;
+        const uint32_t passA = ~fail_ge3(b, st.ca) & o.v;
+        if (machines_on) {
+            if (!it.slow) {
+                // warm-up bookkeeping: 9 consecutive failing windows (all evaluated here) make the state history-free
+                if (!it.emit_on) {
+                    if (x != 0xFFFFFFFFu) st.sync |= SYNC_P;
+                    {
+                        const uint32_t nz = ~passS;
+                        const int lead = ctz32(~nz);  // failing windows at the start of the word
+                        uint32_t e = nz & (nz >> 1); e &= e >> 2; e &= e >> 4; e &= nz >> 8;
+                        if (e || st.zS + lead >= 9) st.sync |= SYNC_S;
+                        const int tr = clz32(~nz);
+                        st.zS = (tr == 32) ? ((st.zS + 32 > 64) ? 64 : st.zS + 32) : tr;
+                    }
+                    {
+                        const uint32_t nz = ~passA;
+                        const int lead = ctz32(~nz);
+                        uint32_t e = nz & (nz >> 1); e &= e >> 2; e &= e >> 4; e &= nz >> 8;
+                        if (e || st.zA + lead >= 9) st.sync |= SYNC_A;
+                        const int tr = clz32(~nz);
+                        st.zA = (tr == 32) ? ((st.zA + 32 > 64) ? 64 : st.zA + 32) : tr;
+                    }
+                }
+                perfect_fast(sk, it, cfg, x, st.pst);
+                win_fast(sk, it, cfg, STREAM_S, passS, st.S);
+                win_fast(sk, it, cfg, STREAM_A, passA, st.A);
+            } else {
+                const int p0 = 32 * it.w;
+                int pv = (int)prev_v31;
+                for (int i = 0; i < 32; ++i) {
+                    const int p = p0 + i;
+                    if (p >= it.L) break;
+                    const int nbit = (o.n >> i) & 1, vbit = (o.v >> i) & 1, xbit = (x >> i) & 1;
+                    // perfect machine, parse_perfect_shiftxor.cpp:175-208
+                    if (nbit) {
+                        if (st.pst != -1) {
+                            if (p - st.pst >= cfg.cutPN) emit_perfect(sk, it, cfg, st.pst, p, p);
+                            st.pst = -1;
+                        }
+                        st.sync |= SYNC_P;
+                    } else if (xbit) {
+                        if (st.pst == -1) st.pst = p;
+                    } else {
+                        if (st.pst != -1 && p - st.pst >= cfg.cutP) emit_perfect(sk, it, cfg, st.pst, p, p);
+                        st.pst = -1;
+                        st.sync |= SYNC_P;
+                    }
+                    win_slow_bit(sk, it, cfg, STREAM_S, p, nbit, vbit, (passS >> i) & 1, st.S, st.zS, st.sync, SYNC_S, pv);
+                    win_slow_bit(sk, it, cfg, STREAM_A, p, nbit, vbit, (passA >> i) & 1, st.A, st.zA, st.sync, SYNC_A, pv);
+                    pv = vbit;
+                }
+            }
+        }
+        st.b_prev = b;
+    }
+    st.x_prev = st.x_cur;
+    st.x_cur = st.x_nxt;
+}
+
+// Tail flush of a motif lane after the last word of the contig.
+template <class Sink>
+RB_HD void lane_tail(Sink& sk, const LaneCfg& cfg, LaneState& st, int L) {
+    if (!cfg.motif) return;
+    // parse_perfect_shiftxor.cpp:213-223: the run that reaches the end is reported with end = L-1
+    if (st.pst != -1 && (L - 1) - st.pst >= cfg.cutP) sk.rec(STREAM_P, st.pst, L - 1, cfg.s, 0, cfg.s << 2);
+    win_tail(sk, cfg, STREAM_S, L, st.S);
+    win_tail(sk, cfg, STREAM_A, L, st.A);
+}
+
+// State of a lane that starts at word q. q == 0 is the true start of the contig (exact); any other q is a cold
+// start whose state becomes exact once the sync bits are set.
+RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int q) {
+    st.x_prev = 0u; st.x_cur = 0u; st.x_nxt = 0u; st.b_prev = 0u; st.lenL = 0;
+    st.cs.z = st.cs.o1 = st.cs.t1 = st.cs.o2 = st.cs.t2 = st.cs.u2 = 0u;
+    st.ca = st.cs;
+    st.pst = -1;
+    st.S.cur = st.S.ls = st.S.le = -1;
+    st.A = st.S;
+    st.sync = (q == 0) ? SYNC_ALL : 0;
+    st.zS = st.zA = 0;
+    if (cfg.s == 0) return;
+    st.x_cur = x_word(cw, q, cfg.s);
+    if (q > 0) {
+        st.x_prev = x_word(cw, q - 1, cfg.s);
+        st.b_prev = st.x_prev;
+        st.cs.z = ~st.x_prev;
+        st.ca.z = ~st.x_prev;
+    }
+}
+
+}  // namespace rb
+#endif

@@ -1,0 +1,159 @@
+// TEST INFRASTRUCTURE — CPU emulation of the scan + merge kernels, lane by lane, built from the very headers the
+// CUDA kernels include (ribbit_b200/csrc/{scan_core,merge_core,layout}.h). It lets the CPU test-suite check the
+// kernel logic against the oracle where no GPU exists. It is not a product path: the product has no CPU fallback.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "layout.h"
+#include "merge_core.h"
+#include "scan_core.h"
+
+using namespace rb;
+
+namespace {
+
+struct ItemOut {
+    std::vector<Rec> rec[3];
+};
+
+struct EmuSink {
+    ItemOut* out;
+    int cnt[3];
+    int dmax[3];
+    void rec(int stream, int start, int end, int mlen, int flags, int key) {
+        Rec r; r.start = start; r.end = end; r.mflags = mlen | (flags << 16); r.key = key;
+        out->rec[stream].push_back(r);
+        cnt[stream]++;
+    }
+    void dropped(int stream, int tw) { if (tw + 1 > dmax[stream]) dmax[stream] = tw + 1; }
+};
+
+void pack(const char* seq, int64_t L, int guard, std::vector<PlaneWord>& pw) {
+    const int64_t nw = (L + 31) / 32;
+    pw.assign((size_t)(1 + nw + guard), PlaneWord{0u, 0u, 0xFFFFFFFFu, 0u});
+    for (int64_t w = 0; w < nw; ++w) {
+        PlaneWord o{0u, 0u, 0u, 0u};
+        for (int i = 0; i < 32; ++i) {
+            const int64_t p = 32 * w + i;
+            if (p >= L) { o.n |= 1u << i; continue; }
+            switch (seq[p]) {
+                case 'A': case 'a': break;
+                case 'C': case 'c': o.l |= 1u << i; break;
+                case 'G': case 'g': o.h |= 1u << i; break;
+                case 'T': case 't': o.h |= 1u << i; o.l |= 1u << i; break;
+                default: o.n |= 1u << i; break;
+            }
+        }
+        pw[(size_t)(1 + w)] = o;
+    }
+    int run = 0;  // consecutive non-N bases ending at p
+    for (int64_t p = 0; p < L; ++p) {
+        const bool isn = (pw[(size_t)(1 + p / 32)].n >> (p & 31)) & 1;
+        run = isn ? 0 : run + 1;
+        if (run >= 8) pw[(size_t)(1 + p / 32)].v |= 1u << (p & 31);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Returns the three ordered streams concatenated per stream: out[stream] malloc'ed arrays of Rec, counts in n[3].
+// restarts (optional) receives the number of warm-up restarts.
+int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, int warm0, Rec** out, int64_t* n,
+             int64_t* restarts) {
+    const BandLayout lay = make_layout(m_lo, m_hi);
+    std::vector<PlaneWord> planes;
+    pack(seq, L, lay.guard, planes);
+    const PlaneWord* cw = planes.data() + 1;
+    const int nw = (int)((L + 31) / 32);
+    if (restarts) *restarts = 0;
+
+    std::vector<Chunk> chunks;
+    if (nw == 0) chunks.push_back(Chunk{0, 0, 0, 1});
+    for (int w = 0; w < nw; w += chunk_words) chunks.push_back(Chunk{0, w, std::min(nw, w + chunk_words), w + chunk_words >= nw});
+
+    std::vector<std::vector<Meta>> meta(lay.nbands, std::vector<Meta>((size_t)nw + 1, Meta{0u, 0u}));
+    std::vector<ItemOut> items(chunks.size() * lay.nbands);
+
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk ch = chunks[ci];
+        for (int band = 0; band < lay.nbands; ++band) {
+            ItemOut& io = items[ci * lay.nbands + band];
+            LaneCfg cfg[32];
+            LaneState st[32];
+            for (int j = 0; j < lay.bw; ++j) cfg[j] = band_lane_cfg(lay, band, j);
+            int H = warm0;
+            for (;;) {
+                io.rec[0].clear(); io.rec[1].clear(); io.rec[2].clear();
+                const int q = std::max(0, ch.w0 - H);
+                const int Ha = (q == 0) ? 0 : std::max(2, (ch.w0 - q) / 2);
+                for (int j = 0; j < lay.bw; ++j) lane_init(cfg[j], st[j], cw, q);
+                bool restart = false;
+                for (int w = q; w < ch.w1 && !restart; ++w) {
+                    uint32_t a[32 + 4] = {0};
+                    for (int j = 0; j < lay.bw; ++j) a[j + 2] = lane_phase1(cfg[j], st[j], cw, w, (int)L);
+                    if (q > 0 && w == q + Ha - 2)
+                        for (int j = 0; j < lay.bw; ++j) if (cfg[j].s && !(st[j].sync & SYNC_X)) restart = true;
+                    if (q > 0 && w == ch.w0)
+                        for (int j = 0; j < lay.bw; ++j) if (cfg[j].motif && (st[j].sync & SYNC_ALL) != SYNC_ALL) restart = true;
+                    if (restart) break;
+                    IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= ch.w0; it.slow = cw[w].v != 0xFFFFFFFFu;
+                    EmuSink sk; sk.out = &io; sk.cnt[0] = sk.cnt[1] = sk.cnt[2] = 0; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                    for (int j = 0; j < lay.bw; ++j)
+                        lane_phase2(sk, cfg[j], st[j], cw, it, j >= 2 ? a[j] : 0u, j >= 1 ? a[j + 1] : 0u,
+                                    j + 1 < lay.bw ? a[j + 3] : 0u, j + 2 < lay.bw ? a[j + 4] : 0u, w >= q + Ha);
+                    if (it.emit_on) meta[band][w] = make_meta(sk.cnt[0], sk.cnt[1], sk.cnt[2], sk.dmax[1], sk.dmax[2], it.slow);
+                }
+                if (!restart) {
+                    if (ch.last) {
+                        EmuSink sk; sk.out = &io; sk.cnt[0] = sk.cnt[1] = sk.cnt[2] = 0; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                        for (int j = 0; j < lay.bw; ++j) lane_tail(sk, cfg[j], st[j], (int)L);
+                        meta[band][nw] = make_meta(sk.cnt[0], sk.cnt[1], sk.cnt[2], 0, 0, 1);
+                    }
+                    break;
+                }
+                if (restarts) ++*restarts;
+                H = std::min(H * 4, ch.w0);
+                if (H < 1) H = 1;
+            }
+        }
+    }
+
+    // merge: buckets in word order
+    std::vector<const Meta*> mp(lay.nbands);
+    for (int b = 0; b < lay.nbands; ++b) mp[b] = meta[b].data();
+    for (int stream = 0; stream < 3; ++stream) {
+        std::vector<Rec> res;
+        for (size_t ci = 0; ci < chunks.size(); ++ci) {
+            const Chunk ch = chunks[ci];
+            std::vector<size_t> off(lay.nbands, 0);
+            const int wend = ch.last ? ch.w1 + 1 : ch.w1;
+            for (int w = ch.w0; w < wend; ++w) {
+                std::vector<const Rec*> src(lay.nbands);
+                std::vector<int> cnt(lay.nbands);
+                int total = 0, slow = 0;
+                for (int b = 0; b < lay.nbands; ++b) {
+                    cnt[b] = meta_cnt(meta[b][w], stream);
+                    src[b] = items[ci * lay.nbands + b].rec[stream].data() + off[b];
+                    off[b] += cnt[b];
+                    total += cnt[b];
+                    slow |= meta_slow(meta[b][w]);
+                }
+                const size_t base = res.size();
+                res.resize(base + total + (bucket_has_pseudo(stream, slow, total) ? 1 : 0));
+                merge_bucket(res.data() + base, src.data(), cnt.data(), lay.nbands, stream, slow, w, mp.data());
+            }
+        }
+        n[stream] = (int64_t)res.size();
+        out[stream] = (Rec*)malloc(std::max<size_t>(1, res.size()) * sizeof(Rec));
+        memcpy(out[stream], res.data(), res.size() * sizeof(Rec));
+    }
+    return 0;
+}
+
+void emu_free(void* p) { free(p); }
+}

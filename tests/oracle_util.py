@@ -1,7 +1,7 @@
 """Test-side access to the parity oracle (oracle/). TEST INFRASTRUCTURE only.
 
 * ``scan_events(seq, m_lo, m_hi)``: CP1 streams from the plain-C restatement
-  (oracle/scan_oracle.c), as an int32 array of rows (stream, start, end, mlen).
+  (oracle/scan_oracle.c), as an int32 array of rows (stream, start, end, mlen, time); time = position at which the reference makes the call, -1 for the tail flush.
 * ``ref_cp(fasta_path, args)``: runs oracle/_ref/ribbit_ref_cp (the unmodified
   reference sources with checkpoint logging) and returns per-contig CP1/CP2
   arrays plus the BED bytes. Only available where oracle/_ref was built.
@@ -22,7 +22,7 @@ REF_CP_BIN = os.path.join(ORACLE_DIR, "_ref", "ribbit_ref_cp")
 
 class _Ev(ctypes.Structure):
     _fields_ = [("stream", ctypes.c_int32), ("start", ctypes.c_int32), ("end", ctypes.c_int32),
-                ("mlen", ctypes.c_int32)]
+                ("mlen", ctypes.c_int32), ("time", ctypes.c_int32)]
 
 
 _lib = None
@@ -62,9 +62,9 @@ def scan_events(seq: bytes, m_lo: int = 2, m_hi: int = 100) -> np.ndarray:
     if n < 0:
         raise MemoryError("rbo_scan failed")
     if n == 0:
-        out = np.zeros((0, 4), dtype=np.int32)
+        out = np.zeros((0, 5), dtype=np.int32)
     else:
-        out = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_int32)), shape=(n, 4)).copy()
+        out = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_int32)), shape=(n, 5)).copy()
     lib.rbo_free(p)
     return out
 

@@ -1,0 +1,100 @@
+"""Expected contents of the library's candidate streams, derived from the oracle's raw CP1 events.
+
+The C ABI (include/ribbit_scan.h) documents the stream encoding; this module restates it for the tests:
+
+* every raw candidate (start, end, mlen) the reference passes to addSeedToSeedPositions* either
+  - is kept (end-start >= the consumer's cutoff, or any perfect candidate)  -> record, flags 0
+  - is below the cutoff and was emitted from a *slow* word (a word whose 8-base windows are not all valid, i.e.
+    near an N / the contig ends) or from the tail flush                      -> record, flags DROPPED
+  - is below the cutoff and was emitted from a fast word                     -> elided
+* anchored tail-flush calls whose returned cursors the reference discards (parse_anchored_shiftxor.cpp:688-719)
+  carry NOCOMMIT when kept and are elided when below the cutoff
+* in front of every non-empty slow bucket of the substitution / anchored stream sits a PSEUDO record whose `end`
+  is the largest end among the candidates elided before it (-1 if none).
+"""
+import numpy as np
+
+DROPPED, PSEUDO, NOCOMMIT = 1, 2, 4
+
+
+def cut_subst(m):
+    return m // 3 if m > 30 else 10
+
+
+def cut_anch(m):
+    c = m if m > 6 else 10
+    if m >= 10:
+        c = int(0.9 * m)
+    return c
+
+
+def valid_words(seq: bytes):
+    """v plane as per scan_core.h: v[p] = p>=7, no N in [p-7,p]; returns bool per word: all 32 bits set."""
+    L = len(seq)
+    a = np.frombuffer(seq, dtype=np.uint8)
+    isn = ~np.isin(a, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+    run = np.zeros(L, dtype=np.int64)
+    # consecutive non-N count
+    idx = np.arange(L)
+    lastn = np.maximum.accumulate(np.where(isn, idx, -1))
+    run = idx - lastn
+    v = run >= 8
+    nw = (L + 31) // 32
+    vv = np.zeros(nw * 32, dtype=bool)
+    vv[:L] = v
+    return vv.reshape(nw, 32).all(axis=1) if nw else np.zeros(0, dtype=bool)
+
+
+def expected_streams(seq: bytes, events: np.ndarray):
+    """events: oracle rows (stream 1..3, start, end, mlen, time). Returns dict stream->(n,5) rows
+    (start, end, mlen, flags, time)."""
+    L = len(seq)
+    nw = (L + 31) // 32
+    fast = valid_words(seq)
+    out = {}
+    for stream in (1, 2, 3):
+        ev = events[events[:, 0] == stream]
+        rows = []
+        last_elided_time = -1  # latest emission time among elided candidates so far (regular: end = time-8)
+        cur_bucket = None
+        pending_pseudo = None
+        # anchored tail: per motif, which calls commit
+        tail = ev[ev[:, 4] == -1]
+        tail_counts = {}
+        for r in tail:
+            tail_counts[int(r[3])] = tail_counts.get(int(r[3]), 0) + 1
+        tail_seen = {}
+        for st, s, e, m, t in ev[:, :5].tolist():
+            is_tail = t == -1
+            bucket = nw if is_tail else t >> 5
+            slow = True if is_tail else not bool(fast[bucket])
+            if stream == 1:
+                rows.append((s, e, m, 0, 32 * nw if is_tail else t))
+                continue
+            cut = cut_subst(m) if stream == 2 else cut_anch(m)
+            kept = (e - s) >= cut
+            flags = 0
+            if stream == 3 and is_tail:
+                k = tail_seen.get(m, 0)
+                tail_seen[m] = k + 1
+                commit = tail_counts[m] == 2 and k == 0
+                if not commit:
+                    flags |= NOCOMMIT
+            if not kept:
+                if flags & NOCOMMIT:
+                    continue
+                if not slow:
+                    last_elided_time = max(last_elided_time, t)
+                    continue
+                flags |= DROPPED
+            if slow and bucket != cur_bucket:
+                # pseudo record in front of the first record of a slow bucket
+                pe = -1
+                if last_elided_time >= 0:
+                    # only elided candidates of earlier buckets count
+                    pe = last_elided_time - 8
+                rows.append((-1, pe, 0, PSEUDO, 32 * bucket))
+            cur_bucket = bucket
+            rows.append((s, e, m, flags, 32 * nw if is_tail else t))
+        out[stream] = np.array(rows, dtype=np.int64).reshape(-1, 5)
+    return out
