@@ -1,0 +1,148 @@
+/* ribbit-b200 — C ABI of the B200 seed-scanning library (libribbit_scan.so).
+ *
+ * This is the drop-in boundary for ribbit's tandem-repeat seed-scanning hot path. The reference has no FFI; the path
+ * sits inside processSequence (/root/reference/fasta_utils.cpp:78-170), which packs the contig, builds one match plane
+ * per shift and calls
+ *     processShiftXORsPerfect             parse_perfect_shiftxor.h:10      (parse_perfect_shiftxor.cpp:146)
+ *     processShiftXORswithSubstitutions   parse_substitute_shiftxor.h:9    (parse_substitute_shiftxor.cpp:391)
+ *     generateAnchoredShiftXORs           parse_anchored_shiftxor.h:10     (parse_anchored_shiftxor.cpp:20)
+ *     processShiftXORsAnchored            parse_anchored_shiftxor.h:14     (parse_anchored_shiftxor.cpp:538)
+ * Those scan loops hand every candidate interval, one at a time and in a fixed order, to the order-dependent host
+ * merges addSeedToSeedPositions{Perfect,Substitutions,Anchored} (parse_perfect_shiftxor.cpp:47,
+ * parse_substitute_shiftxor.cpp:18, parse_anchored_shiftxor.cpp:113). This library replaces everything up to that
+ * hand-off: it returns, per contig, the three candidate streams in exactly the reference's call order.
+ *
+ * There is no CPU fallback behind this ABI: rb_create fails when no CUDA device is usable.
+ * Plain C types only; one context per GPU, one host thread per context.
+ */
+#ifndef RIBBIT_SCAN_H
+#define RIBBIT_SCAN_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+/* error codes (negative returns) */
+#define RB_OK 0
+#define RB_E_ARG (-1)      /* bad argument */
+#define RB_E_CUDA (-2)     /* CUDA runtime error; rb_last_error() has the text */
+#define RB_E_NOMEM (-3)    /* host or device allocation failed */
+#define RB_E_STATE (-4)    /* call order violated (e.g. rb_scan before rb_load_contigs) */
+#define RB_E_RANGE (-5)    /* contig too long (>= 2^31 - 2^12 bases) or motif range unsupported */
+
+/* Scan parameters. min_mlen/max_mlen are ribbit's -m / -M (ribbit.cpp:85-86); shifts are derived as
+ * ribbit.cpp:240-243. The remaining reference constants are fixed in the reference (window 8, thresholds 7 then 6,
+ * anchor 3: ribbit.cpp:191, fasta_utils.cpp:165) and are therefore not parameters; `-p` is never read by the
+ * reference (ribbit.cpp:92) and has no counterpart here. */
+typedef struct rb_params {
+    int32_t min_mlen;     /* >= 1 */
+    int32_t max_mlen;     /* >= min_mlen, <= 1000 */
+    int32_t chunk_words;  /* 0 = automatic; words (32 bases) of a contig scanned by one warp item */
+    int32_t reserved;     /* must be 0 */
+} rb_params;
+
+/* One candidate record of a stream.
+ *   flags == 0            the reference calls addSeedToSeedPositions*(start, end, mlen, ...) here
+ *   RB_REC_DROPPED        same call, but end-start is below the consumer's length cutoff
+ *                         (parse_substitute_shiftxor.cpp:44, parse_anchored_shiftxor.cpp:153): only its cursor
+ *                         side effect (…:34-42, …:133-151) matters. Such calls are reported only where they can change
+ *                         a later cursor: next to N runs and contig ends; elsewhere they are elided.
+ *   RB_REC_PSEUDO         no reference call; `end` is the largest `end` among the calls elided before this point
+ *                         (-1 if none). The consumer advances its cursors with it. start = -1, mlen = 0.
+ *   RB_REC_NOCOMMIT       anchored tail-flush call whose returned cursors the reference discards
+ *                         (parse_anchored_shiftxor.cpp:688-719).
+ * `time` is the position the reference's scan loop is at when it makes the call (32*ceil(L/32) for the tail flush). */
+typedef struct rb_rec {
+    int32_t start;
+    int32_t end;
+    uint16_t mlen;
+    uint16_t flags;
+    int32_t time;
+} rb_rec;
+#define RB_REC_DROPPED 1
+#define RB_REC_PSEUDO 2
+#define RB_REC_NOCOMMIT 4
+
+#define RB_STREAM_PERFECT 0
+#define RB_STREAM_SUBST 1
+#define RB_STREAM_ANCHORED 2
+
+/* Result of rb_scan/rb_fetch. Arrays are owned by the context (pinned host memory) and stay valid until the next
+ * rb_load_contigs / rb_scan / rb_fetch / rb_destroy. contig_off[s] has n_contigs+1 entries: records of contig c
+ * in stream s are rec[s][contig_off[s][c] .. contig_off[s][c+1]). */
+typedef struct rb_streams {
+    int32_t n_contigs;
+    int32_t reserved;
+    const rb_rec *rec[3];
+    const int64_t *contig_off[3];
+    int64_t n[3];
+} rb_streams;
+
+/* Device timings of the last rb_scan_device, from CUDA events on the context's stream (milliseconds). */
+typedef struct rb_timing {
+    float pack_ms;    /* ASCII -> planes */
+    float scan_ms;    /* match planes + perfect / substitution / anchored machines */
+    float merge_ms;   /* ordered compaction into the three streams */
+    float total_ms;   /* first kernel start -> last kernel end */
+    int32_t launches; /* kernels launched */
+    int32_t restarts; /* warm-up restarts inside the scan (diagnostic) */
+    int32_t retries;  /* scan re-launches because a record buffer was too small */
+    int32_t reserved;
+} rb_timing;
+
+typedef struct rb_ctx rb_ctx;
+
+int rb_abi_version(void);
+
+/* Creates a context on CUDA device `device`. NULL on failure (rb_last_error(NULL)). */
+rb_ctx *rb_create(int device, const rb_params *params);
+void rb_destroy(rb_ctx *ctx);
+
+/* Text of the last error of `ctx` (or of the last failed rb_create when ctx == NULL). Never NULL. */
+const char *rb_last_error(const rb_ctx *ctx);
+
+/* Copies a batch of contigs to the device (host pointer `ascii`; contig i is ascii[offsets[i] .. offsets[i]+lengths[i]))
+ * and packs them (fasta_utils.cpp:90-115). Replaces the previous batch. The caller keeps `ascii`. */
+int rb_load_contigs(rb_ctx *ctx, const char *ascii, const int64_t *offsets, const int32_t *lengths, int32_t n);
+
+/* Same, but `ascii_dev` is a device pointer on this context's device (no copy). The buffer must stay valid until the
+ * next load. Used when the sequence is already resident in HBM. */
+int rb_load_contigs_device(rb_ctx *ctx, const void *ascii_dev, const int64_t *offsets, const int32_t *lengths, int32_t n);
+
+/* Runs pack + scan + ordered compaction on the device; results stay in device memory. */
+int rb_scan_device(rb_ctx *ctx);
+
+/* Copies the streams of the last rb_scan_device to pinned host memory. */
+int rb_fetch(rb_ctx *ctx, rb_streams *out);
+
+/* rb_scan_device + rb_fetch. */
+int rb_scan(rb_ctx *ctx, rb_streams *out);
+
+/* Record counts of the last rb_scan_device without copying the records. */
+int rb_counts(rb_ctx *ctx, int64_t n[3]);
+
+int rb_get_timing(const rb_ctx *ctx, rb_timing *out);
+
+/* Seed filter of processSeed / processSeedMotifWise (parse_seed.cpp:344-367, parse_smallmotif_seed.cpp:216-235):
+ * for each seed (contig, start, end, mlen) returns the N-truncated end and the longest run of 1s of the anchored
+ * plane B_mlen (fasta_utils.cpp:143-161) over [start, end'). */
+typedef struct rb_seed {
+    int32_t contig, start, end, mlen;
+} rb_seed;
+typedef struct rb_seedinfo {
+    int32_t end_trunc;    /* end after truncation at the first N in [start, end + mlen) */
+    int32_t longest_run;  /* longestContinuousMatches (parse_seed.cpp:26-44) */
+} rb_seedinfo;
+int rb_filter_seeds(rb_ctx *ctx, const rb_seed *seeds, int64_t n, rb_seedinfo *out);
+
+/* Copies the packed planes of contig c to host arrays of ceil(L/32) words (bit i of word w = position 32*w+i):
+ * hi/lo = the two code bits (A=00 C=01 G=10 T=11), nn = N plane. Any pointer may be NULL. */
+int rb_get_planes(rb_ctx *ctx, int32_t contig, uint32_t *hi, uint32_t *lo, uint32_t *nn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,450 @@
+// ribbit-b200: C ABI of the scan library (include/ribbit_scan.h). Host-side orchestration only: geometry tables,
+// buffer management, kernel launches, CUDA-event timing. No CPU implementation of the scan exists behind this ABI.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ribbit_scan.h"
+#include "kernels.h"
+
+using namespace rb;
+
+static_assert(sizeof(rb_rec) == sizeof(Rec), "rb_rec and rb::Rec must have the same layout");
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct rb_ctx {
+    int device = 0;
+    rb_params params{};
+    BandLayout lay{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // host geometry
+    std::vector<Contig> contigs;
+    std::vector<long long> plane_start, bucket_base;
+    std::vector<Chunk> chunks;
+    std::vector<long long> item_base;
+    std::vector<int> item_cap;
+    long long raw_cap = 0;
+    long long dst_cap = 0;
+    bool loaded = false, scanned = false;
+    bool ascii_external = false;
+    const void* ascii_dev_ext = nullptr;
+
+    DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
+        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo;
+    DevBatch batch{};
+
+    // pinned host results
+    void* h_rec = nullptr;
+    size_t h_rec_cap = 0;
+    void* h_off = nullptr;
+    size_t h_off_cap = 0;
+    long long* h_small = nullptr;  // pinned: totals[3], counters[2]
+    long long totals[3] = {0, 0, 0};
+    rb_timing timing{};
+};
+
+namespace {
+
+int fail(rb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define RB_CUDA(c, call)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail((c), e_ == cudaErrorMemoryAllocation ? RB_E_NOMEM : RB_E_CUDA, "%s: %s", #call,       \
+                        cudaGetErrorString(e_));                                                              \
+    } while (0)
+
+int ensure(rb_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return RB_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&b.p, std::max<size_t>(bytes, 256));
+        if (e != cudaSuccess) { b.p = nullptr; return fail(c, RB_E_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+        b.cap = std::max<size_t>(bytes, 256);
+    } else {
+        b.cap = want;
+    }
+    return RB_OK;
+}
+
+template <class T>
+int upload(rb_ctx* c, DevBuf& b, const std::vector<T>& v) {
+    const int rc = ensure(c, b, v.size() * sizeof(T));
+    if (rc) return rc;
+    if (!v.empty()) RB_CUDA(c, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return RB_OK;
+}
+
+int ensure_pinned(rb_ctx* c, void*& p, size_t& cap, size_t bytes) {
+    if (bytes <= cap && p) return RB_OK;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    const size_t want = std::max<size_t>(bytes + bytes / 8, 4096);
+    RB_CUDA(c, cudaHostAlloc(&p, want, cudaHostAllocDefault));
+    cap = want;
+    return RB_OK;
+}
+
+// records per word reserved for one (chunk, band) item; an item that needs more triggers an exact re-run
+int records_per_word(const BandLayout& lay, int band) {
+    const int m0 = band_m0(lay, band);
+    return m0 <= 12 ? 12 : 6;
+}
+
+int build_geometry(rb_ctx* c, const int64_t* offsets, const int32_t* lengths, int32_t n) {
+    const BandLayout& lay = c->lay;
+    c->contigs.resize(n);
+    c->plane_start.resize((size_t)n + 1);
+    c->bucket_base.resize((size_t)n + 1);
+    long long pw = 0, nb = 0, total_words = 0;
+    for (int i = 0; i < n; ++i) {
+        if (lengths[i] < 0 || (long long)lengths[i] > 0x7FFFFFFFll - 4096) return fail(c, RB_E_RANGE, "contig %d: length %d out of range", i, lengths[i]);
+        Contig cg;
+        cg.L = lengths[i];
+        cg.nw = (int32_t)(((long long)lengths[i] + 31) / 32);
+        cg.ascii_off = offsets[i];
+        c->plane_start[i] = pw;
+        cg.word_base = pw + 1;
+        pw += 1 + cg.nw + lay.guard;
+        c->bucket_base[i] = nb;
+        nb += cg.nw + 1;
+        total_words += cg.nw;
+        c->contigs[i] = cg;
+    }
+    c->plane_start[n] = pw;
+    c->bucket_base[n] = nb;
+
+    int cw = c->params.chunk_words;
+    if (cw <= 0) {
+        const long long target_chunks = std::max<long long>(1, 148ll * 64 / lay.nbands);
+        cw = (int)std::min<long long>(1 << 20, std::max<long long>(64, (total_words + target_chunks - 1) / target_chunks));
+    }
+    c->chunks.clear();
+    for (int i = 0; i < n; ++i) {
+        const int nw = c->contigs[i].nw;
+        if (nw == 0) { c->chunks.push_back(Chunk{i, 0, 0, 1}); continue; }
+        for (int w = 0; w < nw; w += cw) c->chunks.push_back(Chunk{i, w, std::min(nw, w + cw), w + cw >= nw ? 1 : 0});
+    }
+    return RB_OK;
+}
+
+void size_items(rb_ctx* c, const std::vector<int>* exact_counts) {
+    const BandLayout& lay = c->lay;
+    const size_t n_items = c->chunks.size() * (size_t)lay.nbands;
+    c->item_base.resize(n_items);
+    c->item_cap.resize(n_items);
+    long long base = 0;
+    for (size_t ci = 0; ci < c->chunks.size(); ++ci) {
+        const int words = c->chunks[ci].w1 - c->chunks[ci].w0;
+        for (int b = 0; b < lay.nbands; ++b) {
+            const size_t it = ci * lay.nbands + b;
+            long long cap = 64 + (long long)words * records_per_word(lay, b);
+            if (exact_counts) cap = std::max<long long>(cap, (*exact_counts)[it]);
+            cap = std::min<long long>(cap, 0x7FFFFFF0ll);
+            c->item_base[it] = base;
+            c->item_cap[it] = (int)cap;
+            base += cap;
+        }
+    }
+    c->raw_cap = base;
+}
+
+int upload_geometry(rb_ctx* c) {
+    int rc;
+    if ((rc = upload(c, c->d_contigs, c->contigs))) return rc;
+    if ((rc = upload(c, c->d_plane_start, c->plane_start))) return rc;
+    if ((rc = upload(c, c->d_bucket_base, c->bucket_base))) return rc;
+    if ((rc = upload(c, c->d_chunks, c->chunks))) return rc;
+    return RB_OK;
+}
+
+int upload_items(rb_ctx* c) {
+    int rc;
+    if ((rc = upload(c, c->d_item_base, c->item_base))) return rc;
+    if ((rc = upload(c, c->d_item_cap, c->item_cap))) return rc;
+    if (c->raw_cap >= 0xFFFFFFF0ll) return fail(c, RB_E_RANGE, "batch too large: %lld candidate slots (load fewer bases per batch)", c->raw_cap);
+    if ((rc = ensure(c, c->d_raw, (size_t)c->raw_cap * sizeof(Rec)))) return rc;
+    if ((rc = ensure(c, c->d_item_count, c->item_base.size() * sizeof(int)))) return rc;
+    c->batch.item_base = (const long long*)c->d_item_base.p;
+    c->batch.item_cap = (const int*)c->d_item_cap.p;
+    c->batch.item_count = (int*)c->d_item_count.p;
+    c->batch.raw = (Rec*)c->d_raw.p;
+    return RB_OK;
+}
+
+int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
+    int rc;
+    if ((rc = upload_geometry(c))) return rc;
+    size_items(c, nullptr);
+    DevBatch& b = c->batch;
+    b = DevBatch{};
+    b.lay = c->lay;
+    b.n_contigs = n;
+    b.n_chunks = (int)c->chunks.size();
+    b.n_items = (long long)c->chunks.size() * c->lay.nbands;
+    b.n_buckets = c->bucket_base[n];
+    b.n_plane_words = c->plane_start[n];
+    b.warm0 = WARMUP_WORDS;
+    b.n_merge_blocks = (int)((b.n_buckets + MERGE_BLOCK - 1) / MERGE_BLOCK);
+    if ((rc = ensure(c, c->d_planes, (size_t)b.n_plane_words * sizeof(PlaneWord)))) return rc;
+    if ((rc = ensure(c, c->d_meta, (size_t)b.n_buckets * c->lay.nbands * sizeof(Meta)))) return rc;
+    if ((rc = ensure(c, c->d_counters, 4 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->d_partial, ((size_t)b.n_merge_blocks + 1) * sizeof(BlockPartial)))) return rc;
+    if ((rc = ensure(c, c->d_contig_off, 3 * ((size_t)n + 1) * sizeof(long long)))) return rc;
+    if ((rc = ensure(c, c->d_totals, 3 * sizeof(long long)))) return rc;
+    b.ascii = (const uint8_t*)ascii_dev;
+    b.contigs = (const Contig*)c->d_contigs.p;
+    b.plane_start = (const long long*)c->d_plane_start.p;
+    b.bucket_base = (const long long*)c->d_bucket_base.p;
+    b.planes = (PlaneWord*)c->d_planes.p;
+    b.chunks = (const Chunk*)c->d_chunks.p;
+    b.meta = (Meta*)c->d_meta.p;
+    b.counters = (int*)c->d_counters.p;
+    b.partial = (BlockPartial*)c->d_partial.p;
+    b.contig_off = (long long*)c->d_contig_off.p;
+    b.totals = (long long*)c->d_totals.p;
+    if ((rc = upload_items(c))) return rc;
+    c->loaded = true;
+    c->scanned = false;
+    return RB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rb_abi_version(void) { return RB_ABI_VERSION; }
+
+const char* rb_last_error(const rb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+rb_ctx* rb_create(int device, const rb_params* params) {
+    if (!params || params->min_mlen < 1 || params->max_mlen < params->min_mlen || params->max_mlen > 1000 ||
+        params->max_mlen - params->min_mlen + 1 > 224 || params->reserved != 0 || params->chunk_words < 0) {
+        fail(nullptr, RB_E_ARG, "rb_create: bad parameters (need 1 <= min_mlen <= max_mlen <= 1000, at most 224 motif sizes)");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        fail(nullptr, RB_E_CUDA, "rb_create: CUDA device %d not available (%s); this library has no CPU path", device,
+             e != cudaSuccess ? cudaGetErrorString(e) : "no such device");
+        return nullptr;
+    }
+    rb_ctx* c = new rb_ctx();
+    c->device = device;
+    c->params = *params;
+    c->lay = make_layout(params->min_mlen, params->max_mlen);
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 5; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    if (ok) ok = cudaHostAlloc((void**)&c->h_small, 8 * sizeof(long long), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        fail(nullptr, RB_E_CUDA, "rb_create: %s", cudaGetErrorString(cudaGetLastError()));
+        rb_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void rb_destroy(rb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_chunks,
+                      &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_raw, &c->d_counters,
+                      &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (c->h_rec) cudaFreeHost(c->h_rec);
+    if (c->h_off) cudaFreeHost(c->h_off);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rb_load_contigs(rb_ctx* c, const char* ascii, const int64_t* offsets, const int32_t* lengths, int32_t n) {
+    if (!c) return RB_E_ARG;
+    if (n < 0 || (n > 0 && (!ascii || !offsets || !lengths))) return fail(c, RB_E_ARG, "rb_load_contigs: null argument");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    int rc = build_geometry(c, offsets, lengths, n);
+    if (rc) return rc;
+    long long hi = 0;
+    for (int i = 0; i < n; ++i) hi = std::max<long long>(hi, offsets[i] + lengths[i]);
+    if ((rc = ensure(c, c->d_ascii, (size_t)hi + 64))) return rc;
+    if (hi > 0) RB_CUDA(c, cudaMemcpyAsync(c->d_ascii.p, ascii, (size_t)hi, cudaMemcpyHostToDevice, c->stream));
+    c->ascii_external = false;
+    rc = finish_load(c, c->d_ascii.p, n);
+    if (rc) return rc;
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may reuse `ascii` and the geometry vectors
+    return RB_OK;
+}
+
+int rb_load_contigs_device(rb_ctx* c, const void* ascii_dev, const int64_t* offsets, const int32_t* lengths, int32_t n) {
+    if (!c) return RB_E_ARG;
+    if (n < 0 || (n > 0 && (!ascii_dev || !offsets || !lengths))) return fail(c, RB_E_ARG, "rb_load_contigs_device: null argument");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    int rc = build_geometry(c, offsets, lengths, n);
+    if (rc) return rc;
+    c->ascii_external = true;
+    rc = finish_load(c, ascii_dev, n);
+    if (rc) return rc;
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RB_OK;
+}
+
+int rb_scan_device(rb_ctx* c) {
+    if (!c) return RB_E_ARG;
+    if (!c->loaded) return fail(c, RB_E_STATE, "rb_scan_device: no contigs loaded");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    DevBatch& b = c->batch;
+    rb_timing tm{};
+    cudaStream_t st = c->stream;
+    RB_CUDA(c, cudaEventRecord(c->ev[0], st));
+    launch_pack(b, st);
+    tm.launches += b.n_plane_words ? 1 : 0;
+    RB_CUDA(c, cudaEventRecord(c->ev[1], st));
+    for (int attempt = 0;; ++attempt) {
+        RB_CUDA(c, cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), st));
+        launch_scan(b, st);
+        tm.launches += b.n_items ? 1 : 0;
+        if (attempt == 0) RB_CUDA(c, cudaEventRecord(c->ev[2], st));
+        launch_merge_count(b, st);
+        tm.launches += b.n_buckets ? 2 : 0;
+        // stream sizes and the overflow flag are needed on the host to size the final pool
+        RB_CUDA(c, cudaMemcpyAsync(c->h_small, b.totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(c, cudaMemcpyAsync(c->h_small + 4, b.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(c, cudaStreamSynchronize(st));
+        RB_CUDA(c, cudaGetLastError());
+        const int* counters = (const int*)(c->h_small + 4);
+        if (b.n_buckets == 0) { c->h_small[0] = c->h_small[1] = c->h_small[2] = 0; }
+        tm.restarts += counters[1];
+        if (b.n_items == 0 || counters[0] == 0) break;
+        if (attempt >= 2) return fail(c, RB_E_CUDA, "rb_scan_device: candidate buffers still too small after an exact re-run");
+        // some item produced more records than reserved: size every item from the counts and run again
+        std::vector<int> counts(c->item_base.size());
+        RB_CUDA(c, cudaMemcpy(counts.data(), b.item_count, counts.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        size_items(c, &counts);
+        int rc = upload_items(c);
+        if (rc) return rc;
+        ++tm.retries;
+    }
+    for (int s = 0; s < 3; ++s) c->totals[s] = c->h_small[s];
+    const long long total = c->totals[0] + c->totals[1] + c->totals[2];
+    int rc = ensure(c, c->d_dst, (size_t)std::max<long long>(total, 1) * sizeof(Rec));
+    if (rc) return rc;
+    b.dst = (Rec*)c->d_dst.p;
+    launch_merge_write(b, st);
+    tm.launches += b.n_buckets ? 1 : 0;
+    RB_CUDA(c, cudaEventRecord(c->ev[3], st));
+    RB_CUDA(c, cudaStreamSynchronize(st));
+    RB_CUDA(c, cudaGetLastError());
+    RB_CUDA(c, cudaEventElapsedTime(&tm.pack_ms, c->ev[0], c->ev[1]));
+    RB_CUDA(c, cudaEventElapsedTime(&tm.scan_ms, c->ev[1], c->ev[2]));
+    RB_CUDA(c, cudaEventElapsedTime(&tm.merge_ms, c->ev[2], c->ev[3]));
+    RB_CUDA(c, cudaEventElapsedTime(&tm.total_ms, c->ev[0], c->ev[3]));
+    c->timing = tm;
+    c->scanned = true;
+    return RB_OK;
+}
+
+int rb_counts(rb_ctx* c, int64_t n[3]) {
+    if (!c || !n) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_counts: no scan result");
+    for (int s = 0; s < 3; ++s) n[s] = c->totals[s];
+    return RB_OK;
+}
+
+int rb_fetch(rb_ctx* c, rb_streams* out) {
+    if (!c || !out) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_fetch: no scan result");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    const long long total = c->totals[0] + c->totals[1] + c->totals[2];
+    const int n = c->batch.n_contigs;
+    int rc = ensure_pinned(c, c->h_rec, c->h_rec_cap, (size_t)std::max<long long>(total, 1) * sizeof(Rec));
+    if (rc) return rc;
+    rc = ensure_pinned(c, c->h_off, c->h_off_cap, 3 * ((size_t)n + 1) * sizeof(long long));
+    if (rc) return rc;
+    if (total > 0) RB_CUDA(c, cudaMemcpyAsync(c->h_rec, c->d_dst.p, (size_t)total * sizeof(Rec), cudaMemcpyDeviceToHost, c->stream));
+    if (c->batch.n_buckets > 0)
+        RB_CUDA(c, cudaMemcpyAsync(c->h_off, c->d_contig_off.p, 3 * ((size_t)n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    else
+        memset(c->h_off, 0, 3 * ((size_t)n + 1) * sizeof(long long));
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->n_contigs = n;
+    out->reserved = 0;
+    long long base = 0;
+    for (int s = 0; s < 3; ++s) {
+        out->rec[s] = (const rb_rec*)c->h_rec + base;
+        out->contig_off[s] = (const int64_t*)c->h_off + (size_t)s * (n + 1);
+        out->n[s] = c->totals[s];
+        base += c->totals[s];
+    }
+    return RB_OK;
+}
+
+int rb_scan(rb_ctx* c, rb_streams* out) {
+    const int rc = rb_scan_device(c);
+    if (rc) return rc;
+    return rb_fetch(c, out);
+}
+
+int rb_get_timing(const rb_ctx* c, rb_timing* out) {
+    if (!c || !out) return RB_E_ARG;
+    *out = c->timing;
+    return RB_OK;
+}
+
+int rb_get_planes(rb_ctx* c, int32_t contig, uint32_t* hi, uint32_t* lo, uint32_t* nn) {
+    if (!c) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_get_planes: planes exist after rb_scan_device");
+    if (contig < 0 || contig >= c->batch.n_contigs) return fail(c, RB_E_ARG, "rb_get_planes: contig out of range");
+    const Contig& cg = c->contigs[contig];
+    std::vector<PlaneWord> tmp((size_t)cg.nw);
+    if (cg.nw) RB_CUDA(c, cudaMemcpy(tmp.data(), (const PlaneWord*)c->d_planes.p + cg.word_base, tmp.size() * sizeof(PlaneWord), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < cg.nw; ++w) {
+        if (hi) hi[w] = tmp[w].h;
+        if (lo) lo[w] = tmp[w].l;
+        if (nn) {
+            // bits past the contig end are 1 on the device (padding counts as N); report the reference's plane
+            uint32_t m = 0xFFFFFFFFu;
+            const long long rem = (long long)cg.L - 32ll * w;
+            if (rem < 32) m = rem <= 0 ? 0u : ((1u << rem) - 1u);
+            nn[w] = tmp[w].n & m;
+        }
+    }
+    return RB_OK;
+}
+
+int rb_filter_seeds(rb_ctx* c, const rb_seed* seeds, int64_t n, rb_seedinfo* out) {
+    (void)seeds; (void)n; (void)out;
+    return fail(c, RB_E_STATE, "rb_filter_seeds: not available in this build");
+}
+
+}  // extern "C"

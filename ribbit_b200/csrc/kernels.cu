@@ -1,0 +1,415 @@
+// ribbit-b200: sm_100a kernels of the seed-scanning path.
+//   K1 pack_kernel     ASCII -> (h, l, n, v) plane words                 fasta_utils.cpp:78-115
+//   K2 scan_kernel     match words + perfect / substitution / anchored    fasta_utils.cpp:117-161,
+//                      seed machines, one warp lane per shift             parse_{perfect,substitute,anchored}_shiftxor.cpp
+//   K6 merge kernels   ordered compaction of the candidate buckets        call order of addSeedToSeedPositions*
+// The per-lane logic lives in scan_core.h / merge_core.h, which the CPU warp emulator of tests/ compiles too.
+#include "kernels.h"
+
+namespace rb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: one thread per plane word (guard words included).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_segment(const long long* __restrict__ starts, int n, long long x) {
+    // largest c in [0, n) with starts[c] <= x
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(starts + mid) <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(DevBatch b) {
+    const long long pw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pw >= b.n_plane_words) return;
+    const int c = find_segment(b.plane_start, b.n_contigs, pw);
+    const Contig cg = b.contigs[c];
+    const long long w = pw - b.plane_start[c] - 1;  // word of the contig, -1 and >= nw are guard words
+    PlaneWord o;
+    o.h = 0u; o.l = 0u; o.n = 0xFFFFFFFFu; o.v = 0u;
+    if (w >= 0 && w < cg.nw) {
+        const long long p0 = 32 * w;
+        const uint8_t* __restrict__ src = b.ascii + cg.ascii_off;
+        unsigned long long nx = 0ull;  // bit i <-> position p0 - 7 + i
+        uint32_t h = 0u, l = 0u;
+#pragma unroll
+        for (int i = 0; i < 39; ++i) {
+            const long long p = p0 - 7 + i;
+            uint32_t isn = 1u, hb = 0u, lb = 0u;
+            if (p >= 0 && p < cg.L) {
+                const uint32_t x = (uint32_t)__ldg(src + p) | 0x20u;  // fasta_utils.cpp:95-113: either case
+                const uint32_t a = x == 'a', cc = x == 'c', g = x == 'g', t = x == 't';
+                isn = !(a | cc | g | t);
+                hb = g | t;
+                lb = cc | t;
+            }
+            nx |= (unsigned long long)isn << i;
+            if (i >= 7) { h |= hb << (i - 7); l |= lb << (i - 7); }
+        }
+        unsigned long long t = nx;
+        t |= t >> 1; t |= t >> 2; t |= t >> 4;  // bit i: an N among positions p0-7+i .. p0+i
+        o.h = h; o.l = l;
+        o.n = (uint32_t)(nx >> 7);
+        o.v = ~(uint32_t)t;
+    }
+    b.planes[pw] = o;
+}
+
+void launch_pack(const DevBatch& b, cudaStream_t st) {
+    if (b.n_plane_words == 0) return;
+    const long long blocks = (b.n_plane_words + 255) / 256;
+    pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2: scan. A warp holds 32 / BW items (chunk x band); lane j of an item handles shift band_m0 - 2 + j.
+// ---------------------------------------------------------------------------------------------------------------
+struct GpuSink {
+    Rec* base;
+    int cap;
+    int* cnt;
+    uint32_t counts;  // nP | nS << 10 | nA << 20 of this lane in this bucket
+    int dS, dA;
+    __device__ __forceinline__ void rec(int stream, int start, int end, int mlen, int flags, int key) {
+        const int idx = atomicAdd(cnt, 1);
+        if (idx < cap) {
+            int4 v;
+            v.x = start; v.y = end; v.z = mlen | (flags << 16) | (stream << REC_STREAM_SHIFT); v.w = key;
+            *reinterpret_cast<int4*>(base + idx) = v;
+        }
+        counts += 1u << (10 * stream);
+    }
+    __device__ __forceinline__ void dropped(int stream, int tw) {
+        if (stream == STREAM_S) dS = max(dS, tw + 1); else dA = max(dA, tw + 1);
+    }
+};
+
+static const int SCAN_WARPS = 4;
+
+template <int BW>
+__global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
+    constexpr int GROUPS = 32 / BW;
+    __shared__ int s_cnt[SCAN_WARPS][GROUPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / BW, j = lane % BW;
+    const unsigned gmask = (BW == 32) ? 0xFFFFFFFFu : (((1u << BW) - 1u) << (g * BW));
+    const long long item = ((long long)blockIdx.x * SCAN_WARPS + warp) * GROUPS + g;
+    bool active = item < b.n_items;
+    const int nbands = b.lay.nbands;
+    const int band = active ? (int)(item % nbands) : 0;
+    Chunk ch;
+    ch.contig = 0; ch.w0 = 0; ch.w1 = 0; ch.last = 0;
+    if (active) ch = b.chunks[item / nbands];
+    const Contig cg = b.contigs[ch.contig];
+    const PlaneWord* __restrict__ cw = b.planes + cg.word_base;
+    const int L = cg.L;
+    const LaneCfg cfg = band_lane_cfg(b.lay, band, j);
+    Meta* __restrict__ meta = b.meta + (long long)band * b.n_buckets + b.bucket_base[ch.contig];
+    int* cnt = &s_cnt[warp][g];
+
+    GpuSink sk;
+    sk.base = b.raw + (active ? b.item_base[item] : 0);
+    sk.cap = active ? b.item_cap[item] : 0;
+    sk.cnt = cnt;
+    const uint32_t off0 = active ? (uint32_t)b.item_base[item] : 0u;
+
+    LaneState st;
+    int H = b.warm0;
+    int q = max(0, ch.w0 - H);
+    int Ha = (q == 0) ? 0 : max(2, (ch.w0 - q) / 2);
+    lane_init(cfg, st, cw, q);
+    int w = q;
+    if (j == 0) *cnt = 0;
+    __syncwarp();
+    int restarts = 0;
+    if (active && ch.w0 >= ch.w1) {  // empty contig: only the tail bucket
+        active = false;
+        if (ch.last) {
+            if (j == 0) meta[ch.w1] = make_meta(0u, 0, 0, 1, off0);
+        }
+        if (j == 0) b.item_count[item] = 0;
+    }
+
+    while (__any_sync(0xFFFFFFFFu, active)) {
+        uint32_t a = 0u;
+        if (active) a = lane_phase1(cfg, st, cw, w, L);
+        bool bad = false;
+        if (active && q > 0) {
+            if (w == q + Ha - 2 && cfg.s && !(st.sync & SYNC_X)) bad = true;
+            if (w == ch.w0 && cfg.motif && (st.sync & SYNC_ALL) != SYNC_ALL) bad = true;
+        }
+        const unsigned badmask = __ballot_sync(0xFFFFFFFFu, bad) & gmask;
+        // anchor words of the neighbouring shifts (same item): lanes j-2, j-1, j+1, j+2
+        uint32_t a_m2 = __shfl_up_sync(0xFFFFFFFFu, a, 2), a_m1 = __shfl_up_sync(0xFFFFFFFFu, a, 1);
+        uint32_t a_p1 = __shfl_down_sync(0xFFFFFFFFu, a, 1), a_p2 = __shfl_down_sync(0xFFFFFFFFu, a, 2);
+        if (j < 2) a_m2 = 0u;
+        if (j < 1) a_m1 = 0u;
+        if (j + 1 >= BW) a_p1 = 0u;
+        if (j + 2 >= BW) a_p2 = 0u;
+        if (badmask) {
+            // the warm-up did not reach a history-free state: start earlier
+            H = min(H * 4, ch.w0);
+            if (H < 1) H = 1;
+            q = max(0, ch.w0 - H);
+            Ha = (q == 0) ? 0 : max(2, (ch.w0 - q) / 2);
+            lane_init(cfg, st, cw, q);
+            w = q;
+            ++restarts;
+        } else if (active) {
+            IterCtx it;
+            it.w = w; it.L = L; it.emit_on = w >= ch.w0; it.slow = cw[w].v != 0xFFFFFFFFu;
+            sk.counts = 0u; sk.dS = 0; sk.dA = 0;
+            const uint32_t off = off0 + (uint32_t)*cnt;
+            __syncwarp(gmask);
+            lane_phase2(sk, cfg, st, cw, it, a_m2, a_m1, a_p1, a_p2, w >= q + Ha);
+            if (it.emit_on) {
+                const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
+                const int dS = __reduce_max_sync(gmask, sk.dS), dA = __reduce_max_sync(gmask, sk.dA);
+                if (j == 0) meta[w] = make_meta(counts, dS, dA, it.slow, off);
+            }
+            ++w;
+            if (w >= ch.w1) {
+                if (ch.last) {
+                    __syncwarp(gmask);
+                    sk.counts = 0u;
+                    const uint32_t offt = off0 + (uint32_t)*cnt;
+                    __syncwarp(gmask);
+                    lane_tail(sk, cfg, st, L);
+                    const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
+                    if (j == 0) meta[ch.w1] = make_meta(counts, 0, 0, 1, offt);
+                }
+                __syncwarp(gmask);
+                if (j == 0) {
+                    const int n = *cnt;
+                    b.item_count[item] = n;
+                    if (n > sk.cap) atomicAdd(b.counters + 0, 1);
+                    if (restarts) atomicAdd(b.counters + 1, restarts);
+                }
+                active = false;
+            }
+        }
+    }
+}
+
+void launch_scan(const DevBatch& b, cudaStream_t st) {
+    if (b.n_items == 0) return;
+    const int groups = b.lay.groups;
+    const long long warps = (b.n_items + groups - 1) / groups;
+    const unsigned blocks = (unsigned)((warps + SCAN_WARPS - 1) / SCAN_WARPS);
+    if (b.lay.bw == 32) scan_kernel<32><<<blocks, SCAN_WARPS * 32, 0, st>>>(b);
+    else if (b.lay.bw == 16) scan_kernel<16><<<blocks, SCAN_WARPS * 32, 0, st>>>(b);
+    else scan_kernel<8><<<blocks, SCAN_WARPS * 32, 0, st>>>(b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K6: ordered compaction. One thread per bucket (contig word, plus one tail bucket per contig).
+//   M1 merge_count_kernel   per-bucket stream sizes -> per-block sums and elided-end maxima
+//   M2 merge_scan_kernel    exclusive prefix over the blocks (one block)
+//   M3 merge_write_kernel   per-bucket offsets, key ranking, final records
+// ---------------------------------------------------------------------------------------------------------------
+struct BucketInfo {
+    int c, w;
+    unsigned n[3];                  // final records per stream (pseudo included)
+    unsigned pseudo[3];
+    unsigned long long emax[2];     // contig << 32 | elided_end_code
+};
+
+__device__ __forceinline__ BucketInfo bucket_info(const DevBatch& b, long long gb) {
+    BucketInfo bi;
+    bi.c = find_segment(b.bucket_base, b.n_contigs, gb);
+    bi.w = (int)(gb - b.bucket_base[bi.c]);
+    unsigned tot[3] = {0u, 0u, 0u};
+    int slow = 0, dS = 0, dA = 0;
+    for (int k = 0; k < b.lay.nbands; ++k) {
+        const Meta m = b.meta[(long long)k * b.n_buckets + gb];
+        tot[0] += meta_cnt(m, 0); tot[1] += meta_cnt(m, 1); tot[2] += meta_cnt(m, 2);
+        slow |= meta_slow(m);
+        dS = max(dS, meta_dmax(m, STREAM_S));
+        dA = max(dA, meta_dmax(m, STREAM_A));
+    }
+    for (int s = 0; s < 3; ++s) {
+        bi.pseudo[s] = bucket_has_pseudo(s, slow, (int)tot[s]) ? 1u : 0u;
+        bi.n[s] = tot[s] + bi.pseudo[s];
+    }
+    const uint32_t eS = elided_end_code(bi.w, dS), eA = elided_end_code(bi.w, dA);
+    bi.emax[0] = eS ? (((unsigned long long)bi.c << 32) | eS) : 0ull;
+    bi.emax[1] = eA ? (((unsigned long long)bi.c << 32) | eA) : 0ull;
+    return bi;
+}
+
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+// exclusive block scan of (3 sums, 2 maxima); returns the block totals in tot
+__device__ __forceinline__ void block_scan(const unsigned (&n)[3], const unsigned long long (&e)[2], unsigned (&xs)[3],
+                                           unsigned long long (&xe)[2], unsigned (&tot)[3], unsigned long long (&tote)[2]) {
+    __shared__ unsigned s_sum[3][MERGE_BLOCK / 32];
+    __shared__ unsigned long long s_max[2][MERGE_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc[3];
+    unsigned long long ince[2];
+    for (int s = 0; s < 3; ++s) {
+        unsigned v = n[s];
+        for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += t; }
+        inc[s] = v;
+        if (lane == 31) s_sum[s][warp] = v;
+    }
+    for (int s = 0; s < 2; ++s) {
+        unsigned long long v = e[s];
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v = umax64(v, t); }
+        ince[s] = v;
+        if (lane == 31) s_max[s][warp] = v;
+    }
+    __syncthreads();
+    for (int s = 0; s < 3; ++s) {
+        unsigned pre = 0u, all = 0u;
+        for (int k = 0; k < MERGE_BLOCK / 32; ++k) { const unsigned v = s_sum[s][k]; if (k < warp) pre += v; all += v; }
+        xs[s] = pre + inc[s] - n[s];
+        tot[s] = all;
+    }
+    for (int s = 0; s < 2; ++s) {
+        unsigned long long pre = 0ull, all = 0ull;
+        for (int k = 0; k < MERGE_BLOCK / 32; ++k) { const unsigned long long v = s_max[s][k]; if (k < warp) pre = umax64(pre, v); all = umax64(all, v); }
+        const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, ince[s], 1);
+        xe[s] = umax64(pre, lane ? up : 0ull);
+        tote[s] = all;
+    }
+}
+
+__global__ void __launch_bounds__(MERGE_BLOCK) merge_count_kernel(DevBatch b) {
+    const long long gb = (long long)blockIdx.x * MERGE_BLOCK + threadIdx.x;
+    unsigned n[3] = {0u, 0u, 0u};
+    unsigned long long e[2] = {0ull, 0ull};
+    if (gb < b.n_buckets) {
+        const BucketInfo bi = bucket_info(b, gb);
+        for (int s = 0; s < 3; ++s) n[s] = bi.n[s];
+        e[0] = bi.emax[0]; e[1] = bi.emax[1];
+    }
+    unsigned xs[3], tot[3];
+    unsigned long long xe[2], tote[2];
+    block_scan(n, e, xs, xe, tot, tote);
+    if (threadIdx.x == 0) {
+        BlockPartial p;
+        for (int s = 0; s < 3; ++s) p.sum[s] = tot[s];
+        p.emax[0] = tote[0]; p.emax[1] = tote[1];
+        b.partial[blockIdx.x] = p;
+    }
+}
+
+// one block; serial over chunks of 1024 partials, which is plenty (n_merge_blocks ~ n_buckets / 256)
+__global__ void __launch_bounds__(1024) merge_scan_kernel(DevBatch b) {
+    __shared__ unsigned long long s_w[5][32];
+    __shared__ unsigned long long s_carry[5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 5) s_carry[threadIdx.x] = 0ull;
+    __syncthreads();
+    for (int base = 0; base < b.n_merge_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        unsigned long long v[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+        if (i < b.n_merge_blocks) {
+            const BlockPartial p = b.partial[i];
+            v[0] = p.sum[0]; v[1] = p.sum[1]; v[2] = p.sum[2]; v[3] = p.emax[0]; v[4] = p.emax[1];
+        }
+        unsigned long long inc[5];
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long x = v[k];
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if (lane >= d) x = (k < 3) ? x + t : umax64(x, t);
+            }
+            inc[k] = x;
+            if (lane == 31) s_w[k][warp] = x;
+        }
+        __syncthreads();
+        unsigned long long ex[5], all[5];
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long pre = s_carry[k], tot = s_carry[k];
+            for (int u = 0; u < 32; ++u) {
+                const unsigned long long x = s_w[k][u];
+                if (k < 3) { if (u < warp) pre += x; tot += x; }
+                else { if (u < warp) pre = umax64(pre, x); tot = umax64(tot, x); }
+            }
+            if (k < 3) ex[k] = pre + inc[k] - v[k];
+            else {
+                const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, inc[k], 1);
+                ex[k] = umax64(pre, lane ? up : 0ull);
+            }
+            all[k] = tot;
+        }
+        if (i < b.n_merge_blocks) {
+            BlockPartial p;
+            p.sum[0] = ex[0]; p.sum[1] = ex[1]; p.sum[2] = ex[2]; p.emax[0] = ex[3]; p.emax[1] = ex[4];
+            b.partial[i] = p;
+        }
+        __syncthreads();
+        if (threadIdx.x < 5) s_carry[threadIdx.x] = all[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        BlockPartial p;
+        p.sum[0] = s_carry[0]; p.sum[1] = s_carry[1]; p.sum[2] = s_carry[2]; p.emax[0] = s_carry[3]; p.emax[1] = s_carry[4];
+        b.partial[b.n_merge_blocks] = p;
+        b.totals[0] = (long long)s_carry[0]; b.totals[1] = (long long)s_carry[1]; b.totals[2] = (long long)s_carry[2];
+    }
+}
+
+__global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
+    const long long gb = (long long)blockIdx.x * MERGE_BLOCK + threadIdx.x;
+    const bool live = gb < b.n_buckets;
+    BucketInfo bi;
+    bi.c = 0; bi.w = 0;
+    for (int s = 0; s < 3; ++s) { bi.n[s] = 0u; bi.pseudo[s] = 0u; }
+    bi.emax[0] = bi.emax[1] = 0ull;
+    if (live) bi = bucket_info(b, gb);
+    unsigned xs[3], tot[3];
+    unsigned long long xe[2], tote[2];
+    block_scan(bi.n, bi.emax, xs, xe, tot, tote);
+    if (!live) return;
+    const BlockPartial bp = b.partial[blockIdx.x];
+    const BlockPartial total = b.partial[b.n_merge_blocks];
+    long long o[3];  // offsets inside each stream
+    for (int s = 0; s < 3; ++s) o[s] = (long long)bp.sum[s] + xs[s];
+    const long long sbase[3] = {0ll, (long long)total.sum[0], (long long)(total.sum[0] + total.sum[1])};
+    if (bi.w == 0)
+        for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + bi.c] = o[s];
+    if (gb == b.n_buckets - 1)
+        for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + b.n_contigs] = o[s] + bi.n[s];
+    if (bi.n[0] + bi.n[1] + bi.n[2] == 0u) return;
+
+    for (int s = 1; s < 3; ++s)
+        if (bi.pseudo[s]) {
+            const unsigned long long e = umax64(bp.emax[s - 1], xe[s - 1]);
+            long long ee = -1;
+            if (e != 0ull && (int)(e >> 32) == bi.c) ee = (long long)(e & 0xFFFFFFFFull) - 1;
+            const Rec r = pseudo_rec(bi.w, ee);
+            b.dst[sbase[s] + o[s]] = r;
+        }
+    const int nbands = b.lay.nbands;
+    const Rec* src[8];
+    int n[8];
+    for (int k = 0; k < nbands; ++k) {
+        const Meta m = b.meta[(long long)k * b.n_buckets + gb];
+        src[k] = b.raw + m.off;
+        n[k] = meta_total(m);
+    }
+    for (int k = 0; k < nbands; ++k)
+        for (int i = 0; i < n[k]; ++i) {
+            const Rec r = src[k][i];
+            const int s = (r.mflags >> REC_STREAM_SHIFT) & 3;
+            const int rank = rank_in_bucket(r, src, n, nbands);
+            b.dst[sbase[s] + o[s] + bi.pseudo[s] + rank] = finalize_rec(r, bi.w);
+        }
+}
+
+void launch_merge_count(const DevBatch& b, cudaStream_t st) {
+    if (b.n_buckets == 0) return;
+    merge_count_kernel<<<(unsigned)b.n_merge_blocks, MERGE_BLOCK, 0, st>>>(b);
+    merge_scan_kernel<<<1, 1024, 0, st>>>(b);
+}
+void launch_merge_write(const DevBatch& b, cudaStream_t st) {
+    if (b.n_buckets == 0) return;
+    merge_write_kernel<<<(unsigned)b.n_merge_blocks, MERGE_BLOCK, 0, st>>>(b);
+}
+
+}  // namespace rb

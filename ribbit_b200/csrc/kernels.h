@@ -1,0 +1,56 @@
+// ribbit-b200: device-side argument blocks and launch wrappers of the scan library (kernels.cu).
+#ifndef RB_KERNELS_H
+#define RB_KERNELS_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+#include "merge_core.h"
+#include "scan_core.h"
+
+namespace rb {
+
+// per-stream sums + prefix-max codes of one merge block (kernel M1 -> M2 -> M3)
+struct BlockPartial {
+    unsigned long long sum[3];
+    unsigned long long emax[2];  // contig << 32 | elided_end_code, streams S and A
+};
+
+struct DevBatch {
+    BandLayout lay;
+    int n_contigs;
+    int n_chunks;
+    long long n_items;        // n_chunks * nbands
+    long long n_buckets;      // sum over contigs of nw + 1
+    long long n_plane_words;  // plane words including guard words
+    int warm0;
+
+    const uint8_t* ascii;
+    const Contig* contigs;          // [n_contigs]
+    const long long* plane_start;   // [n_contigs + 1] first plane word (the guard word in front) of each contig
+    const long long* bucket_base;   // [n_contigs + 1]
+    PlaneWord* planes;
+    const Chunk* chunks;            // [n_chunks]
+    const long long* item_base;     // [n_items] first raw record of the item
+    const int* item_cap;            // [n_items]
+    int* item_count;                // [n_items] records the item produced (may exceed item_cap: overflow)
+    Meta* meta;                     // [nbands][n_buckets]
+    Rec* raw;                       // raw record pool
+    int* counters;                  // [0] overflowed items, [1] warm-up restarts
+    // merge
+    BlockPartial* partial;          // [n_merge_blocks + 1]; after M2: exclusive prefixes, last = totals
+    int n_merge_blocks;
+    Rec* dst;                       // final pool: stream P, then S, then A
+    long long* contig_off;          // [3][n_contigs + 1]
+    long long* totals;              // [3]
+};
+
+static const int MERGE_BLOCK = 256;
+
+void launch_pack(const DevBatch& b, cudaStream_t st);
+void launch_scan(const DevBatch& b, cudaStream_t st);
+void launch_merge_count(const DevBatch& b, cudaStream_t st);   // M1 + M2
+void launch_merge_write(const DevBatch& b, cudaStream_t st);   // M3
+
+}  // namespace rb
+#endif

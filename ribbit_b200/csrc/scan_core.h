@@ -29,7 +29,7 @@ namespace rb {
 //  n    : N plane (anything that is not ACGTacgt); padding past the contig end is 1
 //  v    : window-valid plane: v[p] = 1 iff p >= 7, p < L and no N in [p-7, p]  (the reference's
 //         `valid_position >= window_length` test, parse_substitute_shiftxor.cpp:469)
-struct PlaneWord {
+struct alignas(16) PlaneWord {
     uint32_t h, l, n, v;
 };
 

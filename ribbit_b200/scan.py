@@ -1,0 +1,212 @@
+"""ctypes binding of the C ABI in include/ribbit_scan.h (libribbit_scan.so) — the reference-facing call a Python
+user makes. Thin: no computation happens here, and there is no CPU fallback; loading fails loudly when the CUDA
+library is missing or no GPU is usable.
+
+The reference's own interface for this path is the group of functions processSequence calls
+(/root/reference/fasta_utils.cpp:117-170); `Scanner.scan` returns what those functions hand to the host merges:
+the three ordered candidate streams (perfect / substitution / anchored), see include/ribbit_scan.h.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libribbit_scan.so")
+
+REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("mlen", "<u2"), ("flags", "<u2"), ("time", "<i4")])
+REC_DROPPED, REC_PSEUDO, REC_NOCOMMIT = 1, 2, 4
+STREAM_NAMES = ("perfect", "subst", "anchored")
+
+EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
+           "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes")
+
+
+class RbParams(ctypes.Structure):
+    _fields_ = [("min_mlen", ctypes.c_int32), ("max_mlen", ctypes.c_int32), ("chunk_words", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+class RbStreams(ctypes.Structure):
+    _fields_ = [("n_contigs", ctypes.c_int32), ("reserved", ctypes.c_int32), ("rec", ctypes.c_void_p * 3),
+                ("contig_off", ctypes.c_void_p * 3), ("n", ctypes.c_int64 * 3)]
+
+
+class RbTiming(ctypes.Structure):
+    _fields_ = [("pack_ms", ctypes.c_float), ("scan_ms", ctypes.c_float), ("merge_ms", ctypes.c_float),
+                ("total_ms", ctypes.c_float), ("launches", ctypes.c_int32), ("restarts", ctypes.c_int32),
+                ("retries", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class RbSeed(ctypes.Structure):
+    _fields_ = [("contig", ctypes.c_int32), ("start", ctypes.c_int32), ("end", ctypes.c_int32), ("mlen", ctypes.c_int32)]
+
+
+class RbSeedInfo(ctypes.Structure):
+    _fields_ = [("end_trunc", ctypes.c_int32), ("longest_run", ctypes.c_int32)]
+
+
+class RibbitScanError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """Loads libribbit_scan.so. Raises if it was not built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RibbitScanError("%s not found: the CUDA library is not built and there is no CPU fallback" % path)
+    lib = ctypes.CDLL(path)
+    lib.rb_abi_version.restype = ctypes.c_int
+    lib.rb_create.restype = ctypes.c_void_p
+    lib.rb_create.argtypes = [ctypes.c_int, ctypes.POINTER(RbParams)]
+    lib.rb_destroy.restype = None
+    lib.rb_destroy.argtypes = [ctypes.c_void_p]
+    lib.rb_last_error.restype = ctypes.c_char_p
+    lib.rb_last_error.argtypes = [ctypes.c_void_p]
+    lib.rb_load_contigs.restype = ctypes.c_int
+    lib.rb_load_contigs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+    lib.rb_load_contigs_device.restype = ctypes.c_int
+    lib.rb_load_contigs_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+    lib.rb_scan_device.restype = ctypes.c_int
+    lib.rb_scan_device.argtypes = [ctypes.c_void_p]
+    lib.rb_fetch.restype = ctypes.c_int
+    lib.rb_fetch.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbStreams)]
+    lib.rb_scan.restype = ctypes.c_int
+    lib.rb_scan.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbStreams)]
+    lib.rb_counts.restype = ctypes.c_int
+    lib.rb_counts.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+    lib.rb_get_timing.restype = ctypes.c_int
+    lib.rb_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbTiming)]
+    lib.rb_filter_seeds.restype = ctypes.c_int
+    lib.rb_filter_seeds.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.rb_get_planes.restype = ctypes.c_int
+    lib.rb_get_planes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    _lib = lib
+    return lib
+
+
+class Scanner:
+    """One scan context on one GPU (rb_ctx). Motif range = ribbit's -m / -M."""
+
+    def __init__(self, min_mlen=2, max_mlen=100, device=0, chunk_words=0):
+        self.lib = load_library()
+        p = RbParams(min_mlen, max_mlen, chunk_words, 0)
+        self.ctx = self.lib.rb_create(device, ctypes.byref(p))
+        if not self.ctx:
+            raise RibbitScanError(self.lib.rb_last_error(None).decode())
+        self.n_contigs = 0
+        self.lengths = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.rb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RibbitScanError("rb error %d: %s" % (rc, self.lib.rb_last_error(self.ctx).decode()))
+
+    @staticmethod
+    def _tables(lengths):
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        offsets = np.zeros(len(lengths), dtype=np.int64)
+        if len(lengths) > 1:
+            offsets[1:] = np.cumsum(lengths[:-1].astype(np.int64))
+        return offsets, lengths
+
+    def load(self, contigs):
+        """contigs: list of bytes (one per contig), host memory. H2D copy + geometry."""
+        lengths = [len(s) for s in contigs]
+        buf = np.frombuffer(b"".join(contigs) + b"\0", dtype=np.uint8)
+        return self.load_flat(buf, lengths)
+
+    def load_flat(self, buf, lengths, offsets=None):
+        """buf: uint8 numpy array (host) holding the contigs back to back (or at `offsets`)."""
+        off, lengths = self._tables(lengths)
+        if offsets is not None:
+            off = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep = (buf, off, lengths)
+        self._check(self.lib.rb_load_contigs(self.ctx, buf.ctypes.data, off.ctypes.data, lengths.ctypes.data, len(lengths)))
+        self.n_contigs = len(lengths)
+        self.lengths = lengths
+
+    def load_device(self, dev_ptr, lengths, offsets=None, keepalive=None):
+        """dev_ptr: integer device address of the ASCII bytes already resident in HBM (e.g. tensor.data_ptr())."""
+        off, lengths = self._tables(lengths)
+        if offsets is not None:
+            off = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep = (keepalive, off, lengths)
+        self._check(self.lib.rb_load_contigs_device(self.ctx, ctypes.c_void_p(dev_ptr), off.ctypes.data, lengths.ctypes.data,
+                                                    len(lengths)))
+        self.n_contigs = len(lengths)
+        self.lengths = lengths
+
+    def scan_device(self):
+        self._check(self.lib.rb_scan_device(self.ctx))
+
+    def counts(self):
+        n = (ctypes.c_int64 * 3)()
+        self._check(self.lib.rb_counts(self.ctx, n))
+        return list(n)
+
+    def fetch(self, copy=True):
+        out = RbStreams()
+        self._check(self.lib.rb_fetch(self.ctx, ctypes.byref(out)))
+        return self._wrap(out, copy)
+
+    def scan(self, copy=True):
+        out = RbStreams()
+        self._check(self.lib.rb_scan(self.ctx, ctypes.byref(out)))
+        return self._wrap(out, copy)
+
+    def _wrap(self, out, copy):
+        res = {}
+        n = out.n_contigs
+        for s in range(3):
+            cnt = out.n[s]
+            if cnt:
+                a = np.ctypeslib.as_array(ctypes.cast(out.rec[s], ctypes.POINTER(ctypes.c_uint8)), shape=(cnt * 16,)).view(REC_DTYPE)
+            else:
+                a = np.zeros(0, dtype=REC_DTYPE)
+            off = np.ctypeslib.as_array(ctypes.cast(out.contig_off[s], ctypes.POINTER(ctypes.c_int64)), shape=(n + 1,))
+            res[s] = (a.copy() if copy else a, off.copy() if copy else off)
+        return res
+
+    def timing(self):
+        t = RbTiming()
+        self._check(self.lib.rb_get_timing(self.ctx, ctypes.byref(t)))
+        return {k: getattr(t, k) for k, _ in RbTiming._fields_ if k != "reserved"}
+
+    def planes(self, contig):
+        nw = (int(self.lengths[contig]) + 31) // 32
+        hi = np.zeros(max(nw, 1), np.uint32); lo = np.zeros(max(nw, 1), np.uint32); nn = np.zeros(max(nw, 1), np.uint32)
+        self._check(self.lib.rb_get_planes(self.ctx, contig, hi.ctypes.data, lo.ctypes.data, nn.ctypes.data))
+        return hi[:nw], lo[:nw], nn[:nw]
+
+    def filter_seeds(self, seeds):
+        """seeds: (n,4) int32 rows (contig, start, end, mlen) -> (n,2) int32 rows (end_trunc, longest_run)."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 4)
+        out = np.zeros((len(seeds), 2), dtype=np.int32)
+        self._check(self.lib.rb_filter_seeds(self.ctx, seeds.ctypes.data, len(seeds), out.ctypes.data))
+        return out
+
+
+def contig_streams(res, contig):
+    """Rows (start, end, mlen, flags, time) of one contig per stream, from Scanner.scan() output."""
+    out = {}
+    for s in range(3):
+        a, off = res[s]
+        r = a[off[contig]:off[contig + 1]]
+        out[s + 1] = np.stack([r["start"], r["end"], r["mlen"], r["flags"], r["time"]], axis=1).astype(np.int64) if len(r) else np.zeros((0, 5), np.int64)
+    return out

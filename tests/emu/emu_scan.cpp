@@ -16,17 +16,17 @@ using namespace rb;
 namespace {
 
 struct ItemOut {
-    std::vector<Rec> rec[3];
+    std::vector<Rec> raw;  // the three streams interleaved in arrival order, as in the kernel's raw record pool
 };
 
 struct EmuSink {
     ItemOut* out;
-    int cnt[3];
+    uint32_t counts;
     int dmax[3];
     void rec(int stream, int start, int end, int mlen, int flags, int key) {
-        Rec r; r.start = start; r.end = end; r.mflags = mlen | (flags << 16); r.key = key;
-        out->rec[stream].push_back(r);
-        cnt[stream]++;
+        Rec r; r.start = start; r.end = end; r.mflags = mlen | (flags << 16) | (stream << REC_STREAM_SHIFT); r.key = key;
+        out->raw.push_back(r);
+        counts += 1u << (10 * stream);
     }
     void dropped(int stream, int tw) { if (tw + 1 > dmax[stream]) dmax[stream] = tw + 1; }
 };
@@ -76,7 +76,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
     if (nw == 0) chunks.push_back(Chunk{0, 0, 0, 1});
     for (int w = 0; w < nw; w += chunk_words) chunks.push_back(Chunk{0, w, std::min(nw, w + chunk_words), w + chunk_words >= nw});
 
-    std::vector<std::vector<Meta>> meta(lay.nbands, std::vector<Meta>((size_t)nw + 1, Meta{0u, 0u}));
+    std::vector<std::vector<Meta>> meta(lay.nbands, std::vector<Meta>((size_t)nw + 1, Meta{0u, 0u, 0u, 0u}));
     std::vector<ItemOut> items(chunks.size() * lay.nbands);
 
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
@@ -88,7 +88,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
             for (int j = 0; j < lay.bw; ++j) cfg[j] = band_lane_cfg(lay, band, j);
             int H = warm0;
             for (;;) {
-                io.rec[0].clear(); io.rec[1].clear(); io.rec[2].clear();
+                io.raw.clear();
                 const int q = std::max(0, ch.w0 - H);
                 const int Ha = (q == 0) ? 0 : std::max(2, (ch.w0 - q) / 2);
                 for (int j = 0; j < lay.bw; ++j) lane_init(cfg[j], st[j], cw, q);
@@ -102,17 +102,19 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                         for (int j = 0; j < lay.bw; ++j) if (cfg[j].motif && (st[j].sync & SYNC_ALL) != SYNC_ALL) restart = true;
                     if (restart) break;
                     IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= ch.w0; it.slow = cw[w].v != 0xFFFFFFFFu;
-                    EmuSink sk; sk.out = &io; sk.cnt[0] = sk.cnt[1] = sk.cnt[2] = 0; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                    EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                    const uint32_t off = (uint32_t)io.raw.size();
                     for (int j = 0; j < lay.bw; ++j)
                         lane_phase2(sk, cfg[j], st[j], cw, it, j >= 2 ? a[j] : 0u, j >= 1 ? a[j + 1] : 0u,
                                     j + 1 < lay.bw ? a[j + 3] : 0u, j + 2 < lay.bw ? a[j + 4] : 0u, w >= q + Ha);
-                    if (it.emit_on) meta[band][w] = make_meta(sk.cnt[0], sk.cnt[1], sk.cnt[2], sk.dmax[1], sk.dmax[2], it.slow);
+                    if (it.emit_on) meta[band][w] = make_meta(sk.counts, sk.dmax[1], sk.dmax[2], it.slow, off);
                 }
                 if (!restart) {
                     if (ch.last) {
-                        EmuSink sk; sk.out = &io; sk.cnt[0] = sk.cnt[1] = sk.cnt[2] = 0; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                        EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                        const uint32_t off = (uint32_t)io.raw.size();
                         for (int j = 0; j < lay.bw; ++j) lane_tail(sk, cfg[j], st[j], (int)L);
-                        meta[band][nw] = make_meta(sk.cnt[0], sk.cnt[1], sk.cnt[2], 0, 0, 1);
+                        meta[band][nw] = make_meta(sk.counts, 0, 0, 1, off);
                     }
                     break;
                 }
@@ -123,34 +125,46 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
         }
     }
 
-    // merge: buckets in word order
-    std::vector<const Meta*> mp(lay.nbands);
-    for (int b = 0; b < lay.nbands; ++b) mp[b] = meta[b].data();
-    for (int stream = 0; stream < 3; ++stream) {
-        std::vector<Rec> res;
-        for (size_t ci = 0; ci < chunks.size(); ++ci) {
-            const Chunk ch = chunks[ci];
-            std::vector<size_t> off(lay.nbands, 0);
-            const int wend = ch.last ? ch.w1 + 1 : ch.w1;
-            for (int w = ch.w0; w < wend; ++w) {
-                std::vector<const Rec*> src(lay.nbands);
-                std::vector<int> cnt(lay.nbands);
-                int total = 0, slow = 0;
-                for (int b = 0; b < lay.nbands; ++b) {
-                    cnt[b] = meta_cnt(meta[b][w], stream);
-                    src[b] = items[ci * lay.nbands + b].rec[stream].data() + off[b];
-                    off[b] += cnt[b];
-                    total += cnt[b];
-                    slow |= meta_slow(meta[b][w]);
-                }
-                const size_t base = res.size();
-                res.resize(base + total + (bucket_has_pseudo(stream, slow, total) ? 1 : 0));
-                merge_bucket(res.data() + base, src.data(), cnt.data(), lay.nbands, stream, slow, w, mp.data());
+    // merge (kernels M1-M3): buckets in word order; per bucket a pseudo record, then the records ranked by key
+    std::vector<Rec> res[3];
+    long long emax[2] = {0, 0};  // running maximum of elided_end_code (exclusive prefix), streams S and A
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk ch = chunks[ci];
+        const int wend = ch.last ? ch.w1 + 1 : ch.w1;
+        for (int w = ch.w0; w < wend; ++w) {
+            std::vector<const Rec*> src(lay.nbands);
+            std::vector<int> cnt(lay.nbands);
+            int tot[3] = {0, 0, 0}, slow = 0, dS = 0, dA = 0;
+            for (int b = 0; b < lay.nbands; ++b) {
+                const Meta m = meta[b][w];
+                cnt[b] = meta_total(m);
+                src[b] = items[ci * lay.nbands + b].raw.data() + m.off;
+                for (int s = 0; s < 3; ++s) tot[s] += meta_cnt(m, s);
+                slow |= meta_slow(m);
+                dS = std::max(dS, meta_dmax(m, STREAM_S));
+                dA = std::max(dA, meta_dmax(m, STREAM_A));
             }
+            size_t base[3];
+            for (int s = 0; s < 3; ++s) {
+                base[s] = res[s].size();
+                const int ps = bucket_has_pseudo(s, slow, tot[s]);
+                if (ps) { res[s].push_back(pseudo_rec(w, emax[s - 1] - 1)); base[s] += 1; }
+                res[s].resize(base[s] + tot[s]);
+            }
+            for (int b = 0; b < lay.nbands; ++b)
+                for (int i = 0; i < cnt[b]; ++i) {
+                    const Rec r = src[b][i];
+                    const int s = (r.mflags >> REC_STREAM_SHIFT) & 3;
+                    res[s][base[s] + rank_in_bucket(r, src.data(), cnt.data(), lay.nbands)] = finalize_rec(r, w);
+                }
+            emax[0] = std::max<long long>(emax[0], elided_end_code(w, dS));
+            emax[1] = std::max<long long>(emax[1], elided_end_code(w, dA));
         }
-        n[stream] = (int64_t)res.size();
-        out[stream] = (Rec*)malloc(std::max<size_t>(1, res.size()) * sizeof(Rec));
-        memcpy(out[stream], res.data(), res.size() * sizeof(Rec));
+    }
+    for (int stream = 0; stream < 3; ++stream) {
+        n[stream] = (int64_t)res[stream].size();
+        out[stream] = (Rec*)malloc(std::max<size_t>(1, res[stream].size()) * sizeof(Rec));
+        memcpy(out[stream], res[stream].data(), res[stream].size() * sizeof(Rec));
     }
     return 0;
 }

@@ -1,0 +1,40 @@
+"""ctypes access to the CPU warp emulator (tests/emu/emu_scan.cpp): the kernels' lane logic, run lane by lane on the
+CPU. TEST INFRASTRUCTURE — lets the CPU suite check the kernel logic against the oracle where no GPU exists."""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        from ribbit_b200 import build
+        _lib = ctypes.CDLL(build.build_emulator())
+        _lib.emu_scan.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                  ctypes.POINTER(ctypes.c_int64)]
+        _lib.emu_free.argtypes = [ctypes.c_void_p]
+    return _lib
+
+
+def emu_streams(seq: bytes, m_lo: int, m_hi: int, chunk_words: int = 1 << 30, warm0: int = 4):
+    """Returns ({stream: (n,5) rows (start, end, mlen, flags, time)}, warm-up restarts)."""
+    L = lib()
+    out = (ctypes.c_void_p * 3)()
+    n = (ctypes.c_int64 * 3)()
+    rs = ctypes.c_int64()
+    L.emu_scan(seq, len(seq), m_lo, m_hi, chunk_words, warm0, out, n, ctypes.byref(rs))
+    res = {}
+    for s in range(3):
+        if n[s]:
+            a = np.ctypeslib.as_array(ctypes.cast(out[s], ctypes.POINTER(ctypes.c_int32)), shape=(n[s], 4)).copy()
+            rows = np.stack([a[:, 0], a[:, 1], a[:, 2] & 0xFFFF, (a[:, 2] >> 16) & 0xFFF, a[:, 3]], axis=1).astype(np.int64)
+        else:
+            rows = np.zeros((0, 5), np.int64)
+        L.emu_free(out[s])
+        res[s + 1] = rows
+    return res, rs.value
