@@ -126,6 +126,10 @@ int rb_counts(rb_ctx *ctx, int64_t n[3]);
 
 int rb_get_timing(const rb_ctx *ctx, rb_timing *out);
 
+/* Diagnostic for the roofline: LOP3 + funnel-shift operations per second (32 lanes counted per warp instruction)
+ * this GPU sustains, measured with a register-only microbenchmark of the scan's instruction mix. */
+int rb_measure_int_peak(rb_ctx *ctx, double *ops_per_s);
+
 /* Seed filter of processSeed / processSeedMotifWise (parse_seed.cpp:344-367, parse_smallmotif_seed.cpp:216-235):
  * for each seed (contig, start, end, mlen) returns the N-truncated end and the longest run of 1s of the anchored
  * plane B_mlen (fasta_utils.cpp:143-161) over [start, end'). */

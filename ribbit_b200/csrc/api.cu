@@ -442,6 +442,19 @@ int rb_get_planes(rb_ctx* c, int32_t contig, uint32_t* hi, uint32_t* lo, uint32_
     return RB_OK;
 }
 
+int rb_measure_int_peak(rb_ctx* c, double* ops_per_s) {
+    if (!c || !ops_per_s) return RB_E_ARG;
+    RB_CUDA(c, cudaSetDevice(c->device));
+    int sms = 0;
+    RB_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    int rc = ensure(c, c->d_counters, 4 * sizeof(int));
+    if (rc) return rc;
+    *ops_per_s = measure_int_peak(c->stream, (uint32_t*)c->d_counters.p, sms);
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RB_CUDA(c, cudaGetLastError());
+    return RB_OK;
+}
+
 int rb_filter_seeds(rb_ctx* c, const rb_seed* seeds, int64_t n, rb_seedinfo* out) {
     (void)seeds; (void)n; (void)out;
     return fail(c, RB_E_STATE, "rb_filter_seeds: not available in this build");

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             const uint32_t off = off0 + (uint32_t)*cnt;
             __syncwarp(gmask);
             lane_phase2(sk, cfg, st, cw, it, a_m2, a_m1, a_p1, a_p2, w >= q + Ha);
+            __syncwarp(gmask);  // orders this word's shared-memory atomics before the next read of *cnt
             if (it.emit_on) {
                 const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
                 const int dS = __reduce_max_sync(gmask, sk.dS), dA = __reduce_max_sync(gmask, sk.dA);
@@ -410,6 +411,46 @@ void launch_merge_count(const DevBatch& b, cudaStream_t st) {
 void launch_merge_write(const DevBatch& b, cudaStream_t st) {
     if (b.n_buckets == 0) return;
     merge_write_kernel<<<(unsigned)b.n_merge_blocks, MERGE_BLOCK, 0, st>>>(b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Integer-pipe microbenchmark (roofline denominator of the scan): independent chains of funnel shifts and LOP3s,
+// the instruction mix of the bit-sliced scan. 16 ops per thread per inner step.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, uint32_t k) {
+    uint32_t a0 = threadIdx.x, a1 = blockIdx.x, a2 = a0 * 3u + 1u, a3 = a1 * 5u + 2u, a4 = a0 ^ 0x55u, a5 = a1 ^ 0xAAu,
+             a6 = a0 + 77u, a7 = a1 + 99u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a0 = __funnelshift_r(a0, a1, 7); a1 = (a1 & k) ^ a2;
+            a2 = __funnelshift_r(a2, a3, 9); a3 = (a3 | k) ^ a4;
+            a4 = __funnelshift_r(a4, a5, 11); a5 = (a5 & k) ^ a6;
+            a6 = __funnelshift_r(a6, a7, 13); a7 = (a7 | k) ^ a0;
+        }
+    }
+    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x12345678u) out[0] = r;
+}
+
+double measure_int_peak(cudaStream_t st, uint32_t* scratch, int sms) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = sms * 8, iters = 4096;
+    int_peak_kernel<<<blocks, 256, 0, st>>>(scratch, 64, 0x0F0F0F0Fu);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, st);
+        int_peak_kernel<<<blocks, 256, 0, st>>>(scratch, iters, 0x0F0F0F0Fu);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double ops = (double)blocks * 256.0 * iters * 32.0;
+    return ops / (best * 1e-3);
 }
 
 }  // namespace rb

@@ -51,6 +51,8 @@ void launch_pack(const DevBatch& b, cudaStream_t st);
 void launch_scan(const DevBatch& b, cudaStream_t st);
 void launch_merge_count(const DevBatch& b, cudaStream_t st);   // M1 + M2
 void launch_merge_write(const DevBatch& b, cudaStream_t st);   // M3
+// LOP3 + SHF warp-lane operations per second the device sustains (integer-pipe roofline denominator)
+double measure_int_peak(cudaStream_t st, uint32_t* scratch, int sms);
 
 }  // namespace rb
 #endif

@@ -19,7 +19,8 @@ REC_DROPPED, REC_PSEUDO, REC_NOCOMMIT = 1, 2, 4
 STREAM_NAMES = ("perfect", "subst", "anchored")
 
 EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
-           "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes")
+           "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes",
+           "rb_measure_int_peak")
 
 
 class RbParams(ctypes.Structure):
@@ -84,6 +85,8 @@ def load_library(path=LIB_PATH):
     lib.rb_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbTiming)]
     lib.rb_filter_seeds.restype = ctypes.c_int
     lib.rb_filter_seeds.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.rb_measure_int_peak.restype = ctypes.c_int
+    lib.rb_measure_int_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
     lib.rb_get_planes.restype = ctypes.c_int
     lib.rb_get_planes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
@@ -187,6 +190,12 @@ class Scanner:
         t = RbTiming()
         self._check(self.lib.rb_get_timing(self.ctx, ctypes.byref(t)))
         return {k: getattr(t, k) for k, _ in RbTiming._fields_ if k != "reserved"}
+
+    def int_peak(self):
+        """Measured LOP3+SHF lane-operations per second of this GPU (roofline denominator)."""
+        v = ctypes.c_double()
+        self._check(self.lib.rb_measure_int_peak(self.ctx, ctypes.byref(v)))
+        return v.value
 
     def planes(self, contig):
         nw = (int(self.lengths[contig]) + 31) // 32
