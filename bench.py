@@ -224,7 +224,7 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    per_step, scan_ms, pack_ms, merge_ms, launches = [], [], [], [], 0
+    per_step, scan_ms, pack_ms, merge_ms, launches, restarts = [], [], [], [], 0, 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()                     # L2 flush between timed iterations
@@ -233,6 +233,7 @@ def run_gpu(args):
         t = sc.timing()
         per_step.append(t["total_ms"]); scan_ms.append(t["scan_ms"]); pack_ms.append(t["pack_ms"]); merge_ms.append(t["merge_ms"])
         launches += t["launches"]
+        restarts += t["restarts"]
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     clocks = sampler.stop()
@@ -287,7 +288,7 @@ def run_gpu(args):
                        "l2": "flushed (512 MiB write) between timed steps", "timing": "CUDA events on the library stream, max over ranks",
                        "candidates_per_step": counts, "stage_ms": {"pack": float(np.mean(pack_ms)), "scan": scan_ms_avg,
                                                                    "merge": float(np.mean(merge_ms))},
-                       "wall_ms_bracket": wall_ms},
+                       "wall_ms_bracket": wall_ms, "warmup_restarts_per_step": restarts / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gbp/s", "h2d_bytes_per_step": int(L), "d2h_bytes_per_step": d2h,
                     "what": "rb_load_contigs (pinned host ASCII -> HBM) + rb_scan (kernels + D2H of the three streams)"},
@@ -314,7 +315,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--bases", type=int, default=DEFAULT_BASES, help="bases per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=500_000, help="bases per CPU-baseline process")
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="bases per CPU-baseline process")
     ap.add_argument("--ref-sample", type=int, default=500_000, help="bases per process and step for --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":

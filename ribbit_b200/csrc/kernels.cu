@@ -115,10 +115,26 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
     sk.cnt = cnt;
     const uint32_t off0 = active ? (uint32_t)b.item_base[item] : 0u;
 
+    // first word of the run of full-N words that ends right before the chunk (group-parallel backward probe)
+    int nb = ch.w0;
+    {
+        bool go = active && ch.w0 > 0;
+        while (__any_sync(0xFFFFFFFFu, go)) {
+            const int wq = nb - 1 - j;
+            const bool f = go && wq >= 0 && full_n(cw, wq);
+            const unsigned bits = (__ballot_sync(0xFFFFFFFFu, f) & gmask) >> (g * BW);
+            const unsigned inv = ~bits & (BW == 32 ? 0xFFFFFFFFu : ((1u << BW) - 1u));
+            const int c = inv ? __ffs((int)inv) - 1 : BW;
+            if (go) {
+                nb -= c;
+                if (c < BW || nb <= 0) go = false;
+            }
+        }
+    }
     LaneState st;
     int H = b.warm0;
-    int q = max(0, ch.w0 - H);
-    int Ha = (q == 0) ? 0 : max(2, (ch.w0 - q) / 2);
+    int q = warmup_start(ch.w0, nb, H);
+    int Ha = warmup_anchor_words(q, H);
     lane_init(cfg, st, cw, q);
     int w = q;
     if (j == 0) *cnt = 0;
@@ -132,7 +148,21 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
         if (j == 0) b.item_count[item] = 0;
     }
 
+    const int guard = b.lay.guard;
     while (__any_sync(0xFFFFFFFFu, active)) {
+        {   // warming up inside an N run: jump over words whose neighbourhood is all N (scan_core.h, lane_skip)
+            const bool can = active && w >= q + Ha && w < ch.w0 - 2;
+            const int wq = w - 1 + j;
+            const bool f = can && wq < cg.nw + guard && full_n(cw, wq);
+            const unsigned bits = (__ballot_sync(0xFFFFFFFFu, f) & gmask) >> (g * BW);
+            const unsigned inv = ~bits & (BW == 32 ? 0xFFFFFFFFu : ((1u << BW) - 1u));
+            const int r = inv ? __ffs((int)inv) - 1 : BW;
+            const int k = can ? min(r - guard - 1, ch.w0 - 2 - w) : 0;
+            if (k > 0) {
+                w += k;
+                lane_skip(cfg, st, cw, w, k);
+            }
+        }
         uint32_t a = 0u;
         if (active) a = lane_phase1(cfg, st, cw, w, L);
         bool bad = false;
@@ -152,8 +182,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             // the warm-up did not reach a history-free state: start earlier
             H = min(H * 4, ch.w0);
             if (H < 1) H = 1;
-            q = max(0, ch.w0 - H);
-            Ha = (q == 0) ? 0 : max(2, (ch.w0 - q) / 2);
+            q = warmup_start(ch.w0, nb, H);
+            Ha = warmup_anchor_words(q, H);
             lane_init(cfg, st, cw, q);
             w = q;
             ++restarts;

@@ -407,7 +407,9 @@ RB_HD uint32_t lane_phase1(const LaneCfg& cfg, LaneState& st, const PlaneWord* c
     st.x_nxt = x_word(cw, w + 1, cfg.s);
     const uint32_t xa = st.x_cur | anchor_endmask(w, L, cfg.s);
     const uint32_t xan = st.x_nxt | anchor_endmask(w + 1, L, cfg.s);
-    if (xa != 0xFFFFFFFFu) st.sync |= SYNC_X;  // a zero was seen: run lengths are exact from here on
+    // a zero was seen: run lengths are exact from here on; a run already >= 2s long can never be an anchor,
+    // whatever its true length
+    if (xa != 0xFFFFFFFFu || st.lenL >= 2 * cfg.s) st.sync |= SYNC_X;
     return anchor_word(cw, w, L, cfg.s, xa, xan, st.lenL);
 }
 
@@ -471,6 +473,8 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
                     win_slow_bit(sk, it, cfg, STREAM_S, p, nbit, vbit, (passS >> i) & 1, st.S, st.zS, st.sync, SYNC_S, pv);
                     win_slow_bit(sk, it, cfg, STREAM_A, p, nbit, vbit, (passA >> i) & 1, st.A, st.zA, st.sync, SYNC_A, pv);
                     pv = vbit;
+                    // the rest of the word is N (or padding): after one N every machine is idle and further Ns are no-ops
+                    if (nbit && (o.n >> i) == (0xFFFFFFFFu >> i)) break;
                 }
             }
         }
@@ -510,6 +514,29 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
         st.ca.z = ~st.x_prev;
     }
 }
+
+// ---- warm-up across N runs ---------------------------------------------------------------------------------------
+// A word is "full-N" when all its 32 positions are N (or padding). Inside a long N run every match word is all ones
+// (N is code 00, fasta_utils.cpp:109-113), no window is evaluated and every machine is idle, so a warming-up lane
+// may jump over such words: only the anchor-view run length grows. Word w may be skipped when words w-1 .. w+guard
+// are all full-N (guard covers the largest shift, so X_s of the skipped word and of its neighbours is all ones).
+RB_HD int full_n(const PlaneWord* cw, int w) { return cw[w].n == 0xFFFFFFFFu; }
+RB_HD void lane_skip(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w_new, int k) {
+    if (cfg.s == 0) return;
+    const long long l = (long long)st.lenL + 32ll * k;
+    st.lenL = l > LEN_SAT ? LEN_SAT : (int)l;
+    st.x_prev = x_word(cw, w_new - 1, cfg.s);
+    st.x_cur = x_word(cw, w_new, cfg.s);
+}
+// words a warm-up spends in front of the run of full-N words that ends right before the chunk (nb = first word of
+// that run, nb == w0 when there is none): start H words before the run when it is long, else H words before w0.
+static const int NRUN_MIN_WORDS = 16;
+RB_HD int warmup_start(int w0, int nb, int H) {
+    const int anchor = (w0 - nb >= NRUN_MIN_WORDS) ? nb : w0;
+    const int q = anchor - H;
+    return q > 0 ? q : 0;
+}
+RB_HD int warmup_anchor_words(int q, int H) { return (q == 0) ? 0 : (H / 2 > 2 ? H / 2 : 2); }
 
 }  // namespace rb
 #endif

@@ -64,13 +64,14 @@ extern "C" {
 // Returns the three ordered streams concatenated per stream: out[stream] malloc'ed arrays of Rec, counts in n[3].
 // restarts (optional) receives the number of warm-up restarts.
 int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, int warm0, Rec** out, int64_t* n,
-             int64_t* restarts) {
+             int64_t* restarts, int64_t* skips) {
     const BandLayout lay = make_layout(m_lo, m_hi);
     std::vector<PlaneWord> planes;
     pack(seq, L, lay.guard, planes);
     const PlaneWord* cw = planes.data() + 1;
     const int nw = (int)((L + 31) / 32);
     if (restarts) *restarts = 0;
+    if (skips) *skips = 0;
 
     std::vector<Chunk> chunks;
     if (nw == 0) chunks.push_back(Chunk{0, 0, 0, 1});
@@ -87,13 +88,26 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
             LaneState st[32];
             for (int j = 0; j < lay.bw; ++j) cfg[j] = band_lane_cfg(lay, band, j);
             int H = warm0;
+            int nb = ch.w0;  // first word of the run of full-N words that ends right before the chunk
+            while (nb > 0 && full_n(cw, nb - 1)) --nb;
             for (;;) {
                 io.raw.clear();
-                const int q = std::max(0, ch.w0 - H);
-                const int Ha = (q == 0) ? 0 : std::max(2, (ch.w0 - q) / 2);
+                const int q = warmup_start(ch.w0, nb, H);
+                const int Ha = warmup_anchor_words(q, H);
                 for (int j = 0; j < lay.bw; ++j) lane_init(cfg[j], st[j], cw, q);
                 bool restart = false;
-                for (int w = q; w < ch.w1 && !restart; ++w) {
+                for (int w = q; w < ch.w1 && !restart;) {
+                    if (w >= q + Ha && w < ch.w0 - 2) {  // warming up inside an N run: jump
+                        int r = 0;
+                        while (r < lay.bw && w - 1 + r < nw + lay.guard && full_n(cw, w - 1 + r)) ++r;
+                        const int k = std::min(r - lay.guard - 1, ch.w0 - 2 - w);
+                        if (k > 0) {
+                            w += k;
+                            for (int j = 0; j < lay.bw; ++j) lane_skip(cfg[j], st[j], cw, w, k);
+                            if (skips) ++*skips;
+                            continue;
+                        }
+                    }
                     uint32_t a[32 + 4] = {0};
                     for (int j = 0; j < lay.bw; ++j) a[j + 2] = lane_phase1(cfg[j], st[j], cw, w, (int)L);
                     if (q > 0 && w == q + Ha - 2)
@@ -108,6 +122,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                         lane_phase2(sk, cfg[j], st[j], cw, it, j >= 2 ? a[j] : 0u, j >= 1 ? a[j + 1] : 0u,
                                     j + 1 < lay.bw ? a[j + 3] : 0u, j + 2 < lay.bw ? a[j + 4] : 0u, w >= q + Ha);
                     if (it.emit_on) meta[band][w] = make_meta(sk.counts, sk.dmax[1], sk.dmax[2], it.slow, off);
+                    ++w;
                 }
                 if (!restart) {
                     if (ch.last) {

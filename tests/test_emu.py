@@ -47,3 +47,30 @@ def test_emulator_long_repeat_forces_restarts():
     got, rs = emu_util.emu_streams(seq, 2, 40, 16)
     assert rs > 0
     _same(got, exp)
+
+
+def _nrun_contig(rng, L):
+    seq = bytearray(synth.fuzz_contig(rng, L, 0.001))
+    for n in (40, 700, 2500):
+        a = int(rng.integers(300, L - 3000))
+        seq[a:a + n] = b"N" * n
+        m = int(rng.integers(1, 30))
+        rep = (bytes(synth.random_bases(rng, m)) * 300)[:int(rng.integers(20, 250))]
+        seq[a - len(rep):a] = rep                      # a repeat running into the N run
+        rep2 = (bytes(synth.random_bases(rng, m + 1)) * 300)[:int(rng.integers(20, 250))]
+        seq[a + n:a + n + len(rep2)] = rep2            # and one starting right after it
+    return bytes(seq)
+
+
+def test_emulator_chunks_inside_long_n_runs_skip_instead_of_rescanning():
+    rng = np.random.default_rng(9)
+    for trial in range(3):
+        seq = _nrun_contig(rng, 9000)
+        for mlo, mhi in [(2, 100), (1, 6)]:
+            exp = sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi))
+            skips = 0
+            for cw in (3, 11, 40):
+                got, _ = emu_util.emu_streams(seq, mlo, mhi, cw)
+                skips += emu_util.emu_streams.last_skips
+                _same(got, exp)
+            assert skips > 0

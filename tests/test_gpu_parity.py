@@ -66,6 +66,18 @@ def test_long_repeat_restarts(built):
     _same(got, exp)
 
 
+def test_long_n_runs_with_small_chunks(built):
+    from test_emu import _nrun_contig
+    rng = np.random.default_rng(9)
+    for trial in range(3):
+        seq = _nrun_contig(rng, 20000)
+        for mlo, mhi in [(2, 100), (1, 6)]:
+            exp = sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi))
+            for cw in (3, 11, 0):
+                got, _, _ = _scan_one(seq, mlo, mhi, cw)
+                _same(got, exp, "trial %d cw=%d" % (trial, cw))
+
+
 def test_many_contigs_batch(built):
     rng = np.random.default_rng(11)
     contigs = [synth.fuzz_contig(rng, int(L), nd) for L, nd in
