@@ -263,7 +263,7 @@ def run_gpu(args):
 
     if rank == 0:
         scan_ms_avg = float(np.mean(scan_ms))
-        ops_per_launch = OPS_PER_BASE * 32.0 * L            # lane-operations (a warp instruction = 32)
+        ops_per_launch = OPS_PER_BASE * L                   # lane-operations (one 32-bit op in one lane = 32 bases x 1 op)
         achieved = ops_per_launch / (scan_ms_avg * 1e-3)
         peaks = {}
         try:

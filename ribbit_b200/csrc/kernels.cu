@@ -133,10 +133,12 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
     }
     LaneState st;
     int H = b.warm0;
-    int q = warmup_start(ch.w0, nb, H);
+    int we = ch.w0;  // first emitting word of the current warm-up (moves on a fast -> slow transition)
+    int q = warmup_start(we, nb, H);
     int Ha = warmup_anchor_words(q, H);
     lane_init(cfg, st, cw, q);
     int w = q;
+    int prev_slow = 1;
     if (j == 0) *cnt = 0;
     __syncwarp();
     int restarts = 0;
@@ -150,25 +152,37 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
 
     const int guard = b.lay.guard;
     while (__any_sync(0xFFFFFFFFu, active)) {
-        {   // warming up inside an N run: jump over words whose neighbourhood is all N (scan_core.h, lane_skip)
-            const bool can = active && w >= q + Ha && w < ch.w0 - 2;
+        const bool can = active && w >= q + Ha && w < we - 2;
+        if (__any_sync(0xFFFFFFFFu, can)) {
+            // warming up inside an N run: jump over words whose neighbourhood is all N (scan_core.h, lane_skip)
             const int wq = w - 1 + j;
             const bool f = can && wq < cg.nw + guard && full_n(cw, wq);
             const unsigned bits = (__ballot_sync(0xFFFFFFFFu, f) & gmask) >> (g * BW);
             const unsigned inv = ~bits & (BW == 32 ? 0xFFFFFFFFu : ((1u << BW) - 1u));
             const int r = inv ? __ffs((int)inv) - 1 : BW;
-            const int k = can ? min(r - guard - 1, ch.w0 - 2 - w) : 0;
+            const int k = can ? min(r - guard - 1, we - 2 - w) : 0;
             if (k > 0) {
                 w += k;
                 lane_skip(cfg, st, cw, w, k);
             }
+        }
+        int slow = active ? ((w < we) || !word_is_fast(cw, w, cg.nw)) : 1;
+        if (active && slow && !prev_slow) {
+            // fast -> slow: the reference machines' state is rebuilt by a warm-up that ends here
+            we = w; nb = w; H = b.warm0;
+            q = warmup_start(we, nb, H);
+            Ha = warmup_anchor_words(q, H);
+            lane_init(cfg, st, cw, q);
+            w = q;
+            prev_slow = 1;
+            slow = 1;
         }
         uint32_t a = 0u;
         if (active) a = lane_phase1(cfg, st, cw, w, L);
         bool bad = false;
         if (active && q > 0) {
             if (w == q + Ha - 2 && cfg.s && !(st.sync & SYNC_X)) bad = true;
-            if (w == ch.w0 && cfg.motif && (st.sync & SYNC_ALL) != SYNC_ALL) bad = true;
+            if (w == we && cfg.motif && (st.sync & SYNC_ALL) != SYNC_ALL) bad = true;
         }
         const unsigned badmask = __ballot_sync(0xFFFFFFFFu, bad) & gmask;
         // anchor words of the neighbouring shifts (same item): lanes j-2, j-1, j+1, j+2
@@ -180,16 +194,17 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
         if (j + 2 >= BW) a_p2 = 0u;
         if (badmask) {
             // the warm-up did not reach a history-free state: start earlier
-            H = min(H * 4, ch.w0);
+            H = min(H * 4, we);
             if (H < 1) H = 1;
-            q = warmup_start(ch.w0, nb, H);
+            q = warmup_start(we, nb, H);
             Ha = warmup_anchor_words(q, H);
             lane_init(cfg, st, cw, q);
             w = q;
+            prev_slow = 1;
             ++restarts;
         } else if (active) {
             IterCtx it;
-            it.w = w; it.L = L; it.emit_on = w >= ch.w0; it.slow = cw[w].v != 0xFFFFFFFFu;
+            it.w = w; it.L = L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow;
             sk.counts = 0u; sk.dS = 0; sk.dA = 0;
             const uint32_t off = off0 + (uint32_t)*cnt;
             __syncwarp(gmask);
@@ -200,6 +215,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
                 const int dS = __reduce_max_sync(gmask, sk.dS), dA = __reduce_max_sync(gmask, sk.dA);
                 if (j == 0) meta[w] = make_meta(counts, dS, dA, it.slow, off);
             }
+            prev_slow = slow;
             ++w;
             if (w >= ch.w1) {
                 if (ch.last) {

@@ -216,32 +216,65 @@ RB_HD uint32_t fail_ge3(uint32_t y, WinCarry& c) {
     return u3;
 }
 
-// reference window machine state for one motif and one stream (parse_substitute_shiftxor.cpp:408-410)
+// reference window machine state for one motif and one stream (parse_substitute_shiftxor.cpp:408-410); maintained
+// in slow words only
 struct WinState {
     int cur, ls, le;
 };
 
+// Bit-parallel view of the same machine, used in fast words (every window of this word and of the previous word is
+// evaluated). P bit t = the window ending at position t passes. With F = ~P:
+//   R8[t] = F[t-7..t] all set (eight failing windows in a row, i.e. the reference's "gap > 7 windows")
+//   S[t]  = P[t] & R8[t-1]           a component starts: first passing window after >= 8 failing ones
+//   E[t]  = P[t-9] & R8[t-1]         the reference emits the component here: its last run ended with the failing
+//                                    window t-8 (= le), and t is the first window start beyond le
+//                                    (parse_substitute_shiftxor.cpp:475-530)
+// The component emitted at E-bit t is (ls, le) = (ts - 7, t - 8) with ts the latest S bit before t.
+struct EvCarry {
+    uint32_t F, r2, r4, r8, P, S;  // previous word
+    int lastS;                     // position of the latest S bit so far
+};
+RB_HD void ev_step(uint32_t P, EvCarry& c, uint32_t& S, uint32_t& E, uint32_t& Sprev) {
+    const uint32_t F = ~P;
+    const uint32_t r2 = F & fsl(c.F, F, 1);
+    const uint32_t r4 = r2 & fsl(c.r2, r2, 2);
+    const uint32_t r8 = r4 & fsl(c.r4, r4, 4);
+    const uint32_t R81 = fsl(c.r8, r8, 1);
+    S = P & R81;
+    E = fsl(c.P, P, 9) & R81;
+    Sprev = c.S;
+    c.F = F; c.r2 = r2; c.r4 = r4; c.r8 = r8; c.P = P; c.S = S;
+}
+
 struct LaneState {
     uint32_t x_prev, x_cur, x_nxt;  // X_s of words w-1, w, w+1
-    uint32_t b_prev;                // B_m of word w-1
     int lenL;                       // anchor-view run length ending at the end of word w-1
     WinCarry cs, ca;
     int pst;                        // perfect machine: start of the open run or -1 (last_starts)
-    WinState S, A;
+    WinState S, A;                  // valid while the previous word was a slow word
+    EvCarry es, ea;                 // carries always valid; lastS valid while the previous word was a fast word
     // warm-up bookkeeping (chunks that do not start at the contig start)
     int sync;                       // bit0 anchors exact, bit1 perfect, bit2 subst, bit3 anchored
     int zS, zA;                     // consecutive evaluated failing windows (saturating)
 };
 enum : int { SYNC_X = 1, SYNC_P = 2, SYNC_S = 4, SYNC_A = 8, SYNC_ALL = 15 };
 
+// Word w is a FAST word when every window ending in words w-1 and w is evaluated (no N within reach, not at the
+// contig start) and w is not the last word of the contig; all other words are SLOW words and go through the
+// reference's state machines bit by bit. Warm-up words (before the first emitting word) are always processed slow.
+RB_HD int word_is_fast(const PlaneWord* cw, int w, int nw) {
+    return cw[w].v == 0xFFFFFFFFu && cw[w - 1].v == 0xFFFFFFFFu && w != nw - 1;
+}
+
 // Context of one lane iteration; the Sink receives the events.
 //   Sink::rec(stream, start, end, mlen, flags, key)   a record that goes to bucket `w` of the stream
 //   Sink::dropped(stream, tw)                          a fast-word candidate below the cutoff (only its time counts)
 struct IterCtx {
-    int w;        // word (bucket) being processed
-    int L;        // contig length
-    int emit_on;  // 0 while warming up (w < first owned word)
-    int slow;     // 1 if this word goes through the bit-serial path
+    int w;          // word (bucket) being processed
+    int L;          // contig length
+    int emit_on;    // 0 while warming up (w < first emitting word)
+    int slow;       // 1 if this word goes through the bit-serial path
+    int prev_slow;  // 1 if the previous word did
 };
 
 template <class Sink>
@@ -250,8 +283,7 @@ RB_HD void emit_win(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream,
     const int cut = (stream == STREAM_S) ? cfg.cutS : cfg.cutA;
     const int tw = time - 32 * it.w;
     if (le - ls >= cut) sk.rec(stream, ls, le, cfg.s, 0, (tw << 18) | (cfg.s << 2));
-    else if (it.slow) sk.rec(stream, ls, le, cfg.s, REC_DROPPED, (tw << 18) | (cfg.s << 2));
-    else sk.dropped(stream, tw);
+    else sk.rec(stream, ls, le, cfg.s, REC_DROPPED, (tw << 18) | (cfg.s << 2));
 }
 template <class Sink>
 RB_HD void emit_perfect(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int start, int end, int time) {
@@ -259,43 +291,44 @@ RB_HD void emit_perfect(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int sta
     sk.rec(STREAM_P, start, end, cfg.s, 0, ((time - 32 * it.w) << 18) | (cfg.s << 2));
 }
 
-// ---- fast word: all 32 windows ending in this word are evaluated -------------------------------------------------
-// P bit i = window ending at position 32w+i (window start wp = 32w-7+i) passes.
+// ---- fast word -----------------------------------------------------------------------------------------------------
+// Emits the components whose E bit lies in this word and that reach the consumer's length cutoff; the others only
+// contribute their emission time (Sink::dropped). S/E are this word's masks, Sprev the previous word's S mask.
 template <class Sink>
-RB_HD void win_fast(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, uint32_t P, WinState& st) {
-    if (P == 0u && st.cur < 0 && st.le < 0) return;
-    const int base = 32 * it.w - 7;
-    int i = 0;
-    if (st.cur >= 0) {
-        const int ones = ctz32(~P);
-        if (ones >= 32) return;  // the open run covers the whole word
-        if (st.ls < 0) st.ls = st.cur;
-        st.le = base + ones + 7;
-        st.cur = -1;
-        i = ones + 1;
-    }
-    for (;;) {
-        const uint32_t rest = (i < 32) ? (P >> i) : 0u;
-        const int a = rest ? i + ctz32(rest) : 32;
-        if (st.le >= 0) {
-            int e = st.le + 1 - base;  // first window start beyond the last component end
-            if (e < i) e = i;
-            if (a >= e) {
-                if (e >= 32) return;  // emitted by a later word
-                emit_win(sk, it, cfg, stream, st.ls, st.le, base + e + 7);
-                st.ls = -1; st.le = -1;
+RB_HD void win_fast_events(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, uint32_t S, uint32_t E,
+                           uint32_t Sprev, int& lastS) {
+    const int cut = (stream == STREAM_S) ? cfg.cutS : cfg.cutA;
+    const int p0 = 32 * it.w;
+    if (E != 0u && it.emit_on) {
+        // cheap exact pre-filter: a component spanning ts..t has length t - ts - 1; kill the E bits whose S bit is
+        // only 9..12 positions back when that is below the cutoff
+        uint32_t kill = 0u;
+        if (cut >= 9) kill |= fsl(Sprev, S, 9);
+        if (cut >= 10) kill |= fsl(Sprev, S, 10);
+        if (cut >= 11) kill |= fsl(Sprev, S, 11);
+        if (cut >= 12) kill |= fsl(Sprev, S, 12);
+        uint32_t x = E & ~kill, kept = 0u;
+        while (x) {
+            const int i = ctz32(x);
+            x &= x - 1u;
+            const uint32_t sb = S & lowmask(i);
+            const int ts = sb ? p0 + 31 - clz32(sb) : lastS;
+            const int ls = ts - 7, le = p0 + i - 8;
+            if (le - ls >= cut) {
+                sk.rec(stream, ls, le, cfg.s, 0, (i << 18) | (cfg.s << 2));
+                kept |= 1u << i;
             }
         }
-        if (a >= 32) return;
-        st.cur = base + a;
-        const int ones = ctz32(~(P >> a));
-        if (a + ones >= 32) return;  // run still open at the end of the word
-        const int f = a + ones;
-        if (st.ls < 0) st.ls = st.cur;
-        st.le = base + f + 7;
-        st.cur = -1;
-        i = f + 1;
+        const uint32_t el = E & ~kept;
+        if (el) sk.dropped(stream, 31 - clz32(el));
     }
+    if (S) lastS = p0 + 31 - clz32(S);
+}
+
+// lastS of the bit-parallel view from the reference machine's state (slow word -> fast word)
+RB_HD void win_to_fast(const WinState& st, int& lastS) {
+    if (st.ls != -1) lastS = st.ls + 7;
+    else if (st.cur != -1) lastS = st.cur + 7;
 }
 
 template <class Sink>
@@ -421,35 +454,22 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
         const PlaneWord o = cw[it.w];
         const uint32_t x = st.x_cur;
         const uint32_t b = x | a_m2 | a_m1 | a_p1 | a_p2;
-        const uint32_t prev_v31 = cw[it.w - 1].v >> 31;
         const uint32_t passS = ~fail_ge2(x, st.cs) & o.v;
         const uint32_t passA = ~fail_ge3(b, st.ca) & o.v;
+        uint32_t sS, eS, sSp, sA, eA, sAp;
+        ev_step(passS, st.es, sS, eS, sSp);
+        ev_step(passA, st.ea, sA, eA, sAp);
         if (machines_on) {
             if (!it.slow) {
-                // warm-up bookkeeping: 9 consecutive failing windows (all evaluated here) make the state history-free
-                if (!it.emit_on) {
-                    if (x != 0xFFFFFFFFu) st.sync |= SYNC_P;
-                    {
-                        const uint32_t nz = ~passS;
-                        const int lead = ctz32(~nz);  // failing windows at the start of the word
-                        uint32_t e = nz & (nz >> 1); e &= e >> 2; e &= e >> 4; e &= nz >> 8;
-                        if (e || st.zS + lead >= 9) st.sync |= SYNC_S;
-                        const int tr = clz32(~nz);
-                        st.zS = (tr == 32) ? ((st.zS + 32 > 64) ? 64 : st.zS + 32) : tr;
-                    }
-                    {
-                        const uint32_t nz = ~passA;
-                        const int lead = ctz32(~nz);
-                        uint32_t e = nz & (nz >> 1); e &= e >> 2; e &= e >> 4; e &= nz >> 8;
-                        if (e || st.zA + lead >= 9) st.sync |= SYNC_A;
-                        const int tr = clz32(~nz);
-                        st.zA = (tr == 32) ? ((st.zA + 32 > 64) ? 64 : st.zA + 32) : tr;
-                    }
+                if (it.prev_slow) {
+                    win_to_fast(st.S, st.es.lastS);
+                    win_to_fast(st.A, st.ea.lastS);
                 }
                 perfect_fast(sk, it, cfg, x, st.pst);
-                win_fast(sk, it, cfg, STREAM_S, passS, st.S);
-                win_fast(sk, it, cfg, STREAM_A, passA, st.A);
+                win_fast_events(sk, it, cfg, STREAM_S, sS, eS, sSp, st.es.lastS);
+                win_fast_events(sk, it, cfg, STREAM_A, sA, eA, sAp, st.ea.lastS);
             } else {
+                const uint32_t prev_v31 = cw[it.w - 1].v >> 31;
                 const int p0 = 32 * it.w;
                 int pv = (int)prev_v31;
                 for (int i = 0; i < 32; ++i) {
@@ -478,7 +498,6 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
                 }
             }
         }
-        st.b_prev = b;
     }
     st.x_prev = st.x_cur;
     st.x_cur = st.x_nxt;
@@ -497,19 +516,22 @@ RB_HD void lane_tail(Sink& sk, const LaneCfg& cfg, LaneState& st, int L) {
 // State of a lane that starts at word q. q == 0 is the true start of the contig (exact); any other q is a cold
 // start whose state becomes exact once the sync bits are set.
 RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int q) {
-    st.x_prev = 0u; st.x_cur = 0u; st.x_nxt = 0u; st.b_prev = 0u; st.lenL = 0;
+    st.x_prev = 0u; st.x_cur = 0u; st.x_nxt = 0u; st.lenL = 0;
     st.cs.z = st.cs.o1 = st.cs.t1 = st.cs.o2 = st.cs.t2 = st.cs.u2 = 0u;
     st.ca = st.cs;
     st.pst = -1;
     st.S.cur = st.S.ls = st.S.le = -1;
     st.A = st.S;
+    st.es.F = st.es.r2 = st.es.r4 = st.es.r8 = 0xFFFFFFFFu;  // nothing before the contig start: "failing" windows
+    st.es.P = st.es.S = 0u;
+    st.es.lastS = -1;
+    st.ea = st.es;
     st.sync = (q == 0) ? SYNC_ALL : 0;
     st.zS = st.zA = 0;
     if (cfg.s == 0) return;
     st.x_cur = x_word(cw, q, cfg.s);
     if (q > 0) {
         st.x_prev = x_word(cw, q - 1, cfg.s);
-        st.b_prev = st.x_prev;
         st.cs.z = ~st.x_prev;
         st.ca.z = ~st.x_prev;
     }

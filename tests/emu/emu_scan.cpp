@@ -64,7 +64,7 @@ extern "C" {
 // Returns the three ordered streams concatenated per stream: out[stream] malloc'ed arrays of Rec, counts in n[3].
 // restarts (optional) receives the number of warm-up restarts.
 int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, int warm0, Rec** out, int64_t* n,
-             int64_t* restarts, int64_t* skips) {
+             int64_t* restarts, int64_t* skips, int64_t* replays) {
     const BandLayout lay = make_layout(m_lo, m_hi);
     std::vector<PlaneWord> planes;
     pack(seq, L, lay.guard, planes);
@@ -72,6 +72,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
     const int nw = (int)((L + 31) / 32);
     if (restarts) *restarts = 0;
     if (skips) *skips = 0;
+    if (replays) *replays = 0;
 
     std::vector<Chunk> chunks;
     if (nw == 0) chunks.push_back(Chunk{0, 0, 0, 1});
@@ -88,19 +89,20 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
             LaneState st[32];
             for (int j = 0; j < lay.bw; ++j) cfg[j] = band_lane_cfg(lay, band, j);
             int H = warm0;
-            int nb = ch.w0;  // first word of the run of full-N words that ends right before the chunk
+            int we = ch.w0;  // first emitting word of the current warm-up (moves on a fast -> slow transition)
+            int nb = we;     // first word of the run of full-N words that ends right before it
             while (nb > 0 && full_n(cw, nb - 1)) --nb;
             for (;;) {
-                io.raw.clear();
-                const int q = warmup_start(ch.w0, nb, H);
+                const int q = warmup_start(we, nb, H);
                 const int Ha = warmup_anchor_words(q, H);
                 for (int j = 0; j < lay.bw; ++j) lane_init(cfg[j], st[j], cw, q);
-                bool restart = false;
+                bool restart = false, replay = false;
+                int prev_slow = 1;
                 for (int w = q; w < ch.w1 && !restart;) {
-                    if (w >= q + Ha && w < ch.w0 - 2) {  // warming up inside an N run: jump
+                    if (w >= q + Ha && w < we - 2) {  // warming up inside an N run: jump
                         int r = 0;
                         while (r < lay.bw && w - 1 + r < nw + lay.guard && full_n(cw, w - 1 + r)) ++r;
-                        const int k = std::min(r - lay.guard - 1, ch.w0 - 2 - w);
+                        const int k = std::min(r - lay.guard - 1, we - 2 - w);
                         if (k > 0) {
                             w += k;
                             for (int j = 0; j < lay.bw; ++j) lane_skip(cfg[j], st[j], cw, w, k);
@@ -108,22 +110,31 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                             continue;
                         }
                     }
+                    const int slow = (w < we) || !word_is_fast(cw, w, nw);
+                    if (slow && !prev_slow) {
+                        // fast -> slow: the reference machines' state is rebuilt by a warm-up that ends here
+                        we = w; nb = w; H = warm0; replay = true;
+                        if (replays) ++*replays;
+                        break;
+                    }
                     uint32_t a[32 + 4] = {0};
                     for (int j = 0; j < lay.bw; ++j) a[j + 2] = lane_phase1(cfg[j], st[j], cw, w, (int)L);
                     if (q > 0 && w == q + Ha - 2)
                         for (int j = 0; j < lay.bw; ++j) if (cfg[j].s && !(st[j].sync & SYNC_X)) restart = true;
-                    if (q > 0 && w == ch.w0)
+                    if (q > 0 && w == we)
                         for (int j = 0; j < lay.bw; ++j) if (cfg[j].motif && (st[j].sync & SYNC_ALL) != SYNC_ALL) restart = true;
                     if (restart) break;
-                    IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= ch.w0; it.slow = cw[w].v != 0xFFFFFFFFu;
+                    IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow;
                     EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
                     const uint32_t off = (uint32_t)io.raw.size();
                     for (int j = 0; j < lay.bw; ++j)
                         lane_phase2(sk, cfg[j], st[j], cw, it, j >= 2 ? a[j] : 0u, j >= 1 ? a[j + 1] : 0u,
                                     j + 1 < lay.bw ? a[j + 3] : 0u, j + 2 < lay.bw ? a[j + 4] : 0u, w >= q + Ha);
                     if (it.emit_on) meta[band][w] = make_meta(sk.counts, sk.dmax[1], sk.dmax[2], it.slow, off);
+                    prev_slow = slow;
                     ++w;
                 }
+                if (replay) continue;
                 if (!restart) {
                     if (ch.last) {
                         EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
@@ -134,7 +145,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                     break;
                 }
                 if (restarts) ++*restarts;
-                H = std::min(H * 4, ch.w0);
+                H = std::min(H * 4, we);
                 if (H < 1) H = 1;
             }
         }

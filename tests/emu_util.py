@@ -16,7 +16,7 @@ def lib():
         _lib = ctypes.CDLL(build.build_emulator())
         _lib.emu_scan.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
-                                  ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+                                  ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         _lib.emu_free.argtypes = [ctypes.c_void_p]
     return _lib
 
@@ -28,8 +28,10 @@ def emu_streams(seq: bytes, m_lo: int, m_hi: int, chunk_words: int = 1 << 30, wa
     n = (ctypes.c_int64 * 3)()
     rs = ctypes.c_int64()
     sk = ctypes.c_int64()
-    L.emu_scan(seq, len(seq), m_lo, m_hi, chunk_words, warm0, out, n, ctypes.byref(rs), ctypes.byref(sk))
+    rp = ctypes.c_int64()
+    L.emu_scan(seq, len(seq), m_lo, m_hi, chunk_words, warm0, out, n, ctypes.byref(rs), ctypes.byref(sk), ctypes.byref(rp))
     emu_streams.last_skips = sk.value
+    emu_streams.last_replays = rp.value
     res = {}
     for s in range(3):
         if n[s]:

@@ -4,8 +4,9 @@ The C ABI (include/ribbit_scan.h) documents the stream encoding; this module res
 
 * every raw candidate (start, end, mlen) the reference passes to addSeedToSeedPositions* either
   - is kept (end-start >= the consumer's cutoff, or any perfect candidate)  -> record, flags 0
-  - is below the cutoff and was emitted from a *slow* word (a word whose 8-base windows are not all valid, i.e.
-    near an N / the contig ends) or from the tail flush                      -> record, flags DROPPED
+  - is below the cutoff and was emitted from a *slow* word (scan_core.h word_is_fast: a word where, or right
+    after a word where, not all 8-base windows are valid - near an N / the contig start - and the last word of
+    the contig) or from the tail flush                                       -> record, flags DROPPED
   - is below the cutoff and was emitted from a fast word                     -> elided
 * anchored tail-flush calls whose returned cursors the reference discards (parse_anchored_shiftxor.cpp:688-719)
   carry NOCOMMIT when kept and are elided when below the cutoff
@@ -28,21 +29,25 @@ def cut_anch(m):
     return c
 
 
-def valid_words(seq: bytes):
-    """v plane as per scan_core.h: v[p] = p>=7, no N in [p-7,p]; returns bool per word: all 32 bits set."""
+def fast_words(seq: bytes):
+    """bool per word, as scan_core.h word_is_fast: every window ending in words w-1 and w is evaluated
+    (v[p] = p>=7 and no N in [p-7,p]) and w is not the last word of the contig."""
     L = len(seq)
     a = np.frombuffer(seq, dtype=np.uint8)
     isn = ~np.isin(a, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
-    run = np.zeros(L, dtype=np.int64)
-    # consecutive non-N count
     idx = np.arange(L)
-    lastn = np.maximum.accumulate(np.where(isn, idx, -1))
-    run = idx - lastn
-    v = run >= 8
+    lastn = np.maximum.accumulate(np.where(isn, idx, -1)) if L else np.zeros(0, dtype=np.int64)
+    v = (idx - lastn) >= 8
     nw = (L + 31) // 32
     vv = np.zeros(nw * 32, dtype=bool)
     vv[:L] = v
-    return vv.reshape(nw, 32).all(axis=1) if nw else np.zeros(0, dtype=bool)
+    allv = vv.reshape(nw, 32).all(axis=1) if nw else np.zeros(0, dtype=bool)
+    fast = allv.copy()
+    if nw:
+        fast[1:] &= allv[:-1]
+        fast[0] = False
+        fast[nw - 1] = False
+    return fast
 
 
 def expected_streams(seq: bytes, events: np.ndarray):
@@ -50,7 +55,7 @@ def expected_streams(seq: bytes, events: np.ndarray):
     (start, end, mlen, flags, time)."""
     L = len(seq)
     nw = (L + 31) // 32
-    fast = valid_words(seq)
+    fast = fast_words(seq)
     out = {}
     for stream in (1, 2, 3):
         ev = events[events[:, 0] == stream]
