@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
     const Contig cg = b.contigs[ch.contig];
     const PlaneWord* __restrict__ cw = b.planes + cg.word_base;
     const int L = cg.L;
-    const LaneCfg cfg = band_lane_cfg(b.lay, band, j);
+    LaneCfg cfg = band_lane_cfg(b.lay, band, j);
+    lane_cfg_set_contig(cfg, L);
     Meta* __restrict__ meta = b.meta + (long long)band * b.n_buckets + b.bucket_base[ch.contig];
     int* cnt = &s_cnt[warp][g];
 
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
     int Ha = warmup_anchor_words(q, H);
     lane_init(cfg, st, cw, q);
     int w = q;
-    int prev_slow = 1;
+    int prev_slow = 1, fastrun = 0;
+    uint32_t off = off0;  // raw-pool index of the next bucket's first record
     if (j == 0) *cnt = 0;
     __syncwarp();
     int restarts = 0;
@@ -178,7 +180,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             slow = 1;
         }
         uint32_t a = 0u;
-        if (active) a = lane_phase1(cfg, st, cw, w, L);
+        if (active) a = slow ? lane_phase1(cfg, st, cw, w, L) : lane_phase1_fast(cfg, st, cw, w, L);
+        fastrun = slow ? 0 : min(fastrun + 1, 4);
         bool bad = false;
         if (active && q > 0) {
             if (w == q + Ha - 2 && cfg.s && !(st.sync & SYNC_X)) bad = true;
@@ -204,28 +207,23 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             ++restarts;
         } else if (active) {
             IterCtx it;
-            it.w = w; it.L = L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow;
+            it.w = w; it.L = L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
             sk.counts = 0u; sk.dS = 0; sk.dA = 0;
-            const uint32_t off = off0 + (uint32_t)*cnt;
-            __syncwarp(gmask);
             lane_phase2(sk, cfg, st, cw, it, a_m2, a_m1, a_p1, a_p2, w >= q + Ha);
-            __syncwarp(gmask);  // orders this word's shared-memory atomics before the next read of *cnt
             if (it.emit_on) {
                 const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
                 const int dS = __reduce_max_sync(gmask, sk.dS), dA = __reduce_max_sync(gmask, sk.dA);
                 if (j == 0) meta[w] = make_meta(counts, dS, dA, it.slow, off);
+                off += (counts & 0x3FFu) + ((counts >> 10) & 0x3FFu) + (counts >> 20);
             }
             prev_slow = slow;
             ++w;
             if (w >= ch.w1) {
                 if (ch.last) {
-                    __syncwarp(gmask);
                     sk.counts = 0u;
-                    const uint32_t offt = off0 + (uint32_t)*cnt;
-                    __syncwarp(gmask);
                     lane_tail(sk, cfg, st, L);
                     const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
-                    if (j == 0) meta[ch.w1] = make_meta(counts, 0, 0, 1, offt);
+                    if (j == 0) meta[ch.w1] = make_meta(counts, 0, 0, 1, off);
                 }
                 __syncwarp(gmask);
                 if (j == 0) {

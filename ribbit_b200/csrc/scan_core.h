@@ -81,6 +81,14 @@ RB_HD uint32_t fsl(uint32_t lo, uint32_t hi, int k) {
     return k ? (hi << k) | (lo >> (32 - k)) : hi;
 #endif
 }
+// as fsl but 0 <= k <= 32 (k = 32 returns lo, the previous word)
+RB_HD uint32_t fslc(uint32_t lo, uint32_t hi, int k) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_lc(lo, hi, k);
+#else
+    return k >= 32 ? lo : fsl(lo, hi, k);
+#endif
+}
 RB_HD uint32_t lowmask(int nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
 
 struct LaneCfg {
@@ -90,7 +98,25 @@ struct LaneCfg {
     int cutPN;   // perfect cutoff, run closed by an N                            parse_perfect_shiftxor.cpp:179
     int cutS;    // substitution keep cutoff  (m>30 ? m/3 : 10)                   parse_substitute_shiftxor.cpp:423
     int cutA;    // anchored keep cutoff                                          parse_anchored_shiftxor.cpp:572-573
+    int wm;      // first word whose anchor view differs from X_s (positions >= L-s are forced to 1); per contig
+    uint32_t dA; // smear shifts of the anchored keep filter, 6 bits each (smear_shifts)
+    uint32_t dA2;
 };
+
+// Shifts d_0..d_6 (each <= 32) that smear a bit over exactly n positions by doubling: with c_0 = 1,
+// d_i = min(c_i, n - c_i), c_{i+1} = c_i + d_i. Packed 6 bits each: d_0..d_4 in lo, d_5..d_6 in hi.
+// n > 96 cannot be reached with 7 steps of at most 32: returns 0 shifts (filter disabled, exact check per event).
+RB_HD void smear_shifts(int n, uint32_t& lo, uint32_t& hi) {
+    lo = 0u; hi = 0u;
+    if (n < 1 || n > 96) return;
+    int c = 1;
+    for (int i = 0; i < 7; ++i) {
+        int d = (n - c < c) ? n - c : c;
+        if (d > 32) d = 32;
+        if (i < 5) lo |= (uint32_t)d << (6 * i); else hi |= (uint32_t)d << (6 * (i - 5));
+        c += d;
+    }
+}
 
 RB_HD LaneCfg make_lane_cfg(int s, int m_lo, int m_hi, int s_lo, int s_hi, int band_m0, int band_m1) {
     LaneCfg c;
@@ -101,8 +127,12 @@ RB_HD LaneCfg make_lane_cfg(int s, int m_lo, int m_hi, int s_lo, int s_hi, int b
     c.cutS = (s > 30) ? s / 3 : 10;
     c.cutA = (s > 6) ? s : 10;
     if (s >= 10) c.cutA = (int)(0.9 * s);
+    c.wm = 0;
+    smear_shifts(c.cutA, c.dA, c.dA2);
     return c;
 }
+// per-contig part of the lane configuration
+RB_HD void lane_cfg_set_contig(LaneCfg& c, int L) { c.wm = (L - c.s) >> 5; }
 
 // X_s word: bit p set iff code[p] == code[p+s] (zeros are shifted in past the contig end because the padding
 // words are zero)  fasta_utils.cpp:121.  `cw` points at word 0 of the contig; indices -1 .. nw+guard-1 are readable.
@@ -111,6 +141,27 @@ RB_HD uint32_t x_word(const PlaneWord* cw, int w, int s) {
     const PlaneWord o = cw[w], a = cw[w + off], b = cw[w + off + 1];
     const uint32_t th = o.h ^ fsr(a.h, b.h, sh);
     const uint32_t tl = o.l ^ fsr(a.l, b.l, sh);
+    return ~(th | tl);
+}
+
+// h / l halves of plane word `idx`, kept from the previous match-word computation (the "b" operand of word w is
+// the "a" operand of word w+1)
+struct XCache {
+    uint32_t h, l;
+    int idx;
+};
+RB_HD uint32_t x_word_cached(const PlaneWord* cw, int w, int s, XCache& xc) {
+    const int off = s >> 5, sh = s & 31;
+    const PlaneWord o = cw[w];
+    uint32_t ah = xc.h, al = xc.l;
+    if (xc.idx != w + off) {
+        const PlaneWord a = cw[w + off];
+        ah = a.h; al = a.l;
+    }
+    const PlaneWord b = cw[w + off + 1];
+    xc.h = b.h; xc.l = b.l; xc.idx = w + off + 1;
+    const uint32_t th = o.h ^ fsr(ah, b.h, sh);
+    const uint32_t tl = o.l ^ fsr(al, b.l, sh);
     return ~(th | tl);
 }
 
@@ -253,6 +304,8 @@ struct LaneState {
     int pst;                        // perfect machine: start of the open run or -1 (last_starts)
     WinState S, A;                  // valid while the previous word was a slow word
     EvCarry es, ea;                 // carries always valid; lastS valid while the previous word was a fast word
+    uint32_t sm[7];                 // anchored keep filter: previous word of each smear level
+    XCache xc;
     // warm-up bookkeeping (chunks that do not start at the contig start)
     int sync;                       // bit0 anchors exact, bit1 perfect, bit2 subst, bit3 anchored
     int zS, zA;                     // consecutive evaluated failing windows (saturating)
@@ -275,6 +328,7 @@ struct IterCtx {
     int emit_on;    // 0 while warming up (w < first emitting word)
     int slow;       // 1 if this word goes through the bit-serial path
     int prev_slow;  // 1 if the previous word did
+    int fastrun;    // consecutive fast words up to and including this one (saturating)
 };
 
 template <class Sink>
@@ -291,37 +345,50 @@ RB_HD void emit_perfect(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int sta
     sk.rec(STREAM_P, start, end, cfg.s, 0, ((time - 32 * it.w) << 18) | (cfg.s << 2));
 }
 
+// Anchored keep filter. M1[t] = OR of S[t-k], k = 1..cutA: an E bit with M1 set belongs to a component whose S bit
+// is at most cutA positions back, i.e. whose length t - ts - 1 is below the consumer's cutoff
+// (parse_anchored_shiftxor.cpp:153). Exact when the last four words were fast words.
+RB_HD uint32_t smear_step(const LaneCfg& cfg, LaneState& st, uint32_t S, uint32_t Sprev) {
+    uint32_t v = fsl(Sprev, S, 1);
+#define RB_SMEAR_LEVEL(i, d)                                  \
+    {                                                         \
+        const uint32_t nv = v | fslc(st.sm[i], v, (int)(d)); \
+        st.sm[i] = v;                                         \
+        v = nv;                                               \
+    }
+    RB_SMEAR_LEVEL(0, cfg.dA & 63u)
+    RB_SMEAR_LEVEL(1, (cfg.dA >> 6) & 63u)
+    RB_SMEAR_LEVEL(2, (cfg.dA >> 12) & 63u)
+    RB_SMEAR_LEVEL(3, (cfg.dA >> 18) & 63u)
+    RB_SMEAR_LEVEL(4, (cfg.dA >> 24) & 63u)
+    RB_SMEAR_LEVEL(5, cfg.dA2 & 63u)
+    RB_SMEAR_LEVEL(6, (cfg.dA2 >> 6) & 63u)
+#undef RB_SMEAR_LEVEL
+    return cfg.dA ? v : 0u;  // cutoffs outside the smear range: no filtering
+}
+
 // ---- fast word -----------------------------------------------------------------------------------------------------
 // Emits the components whose E bit lies in this word and that reach the consumer's length cutoff; the others only
 // contribute their emission time (Sink::dropped). S/E are this word's masks, Sprev the previous word's S mask.
 template <class Sink>
 RB_HD void win_fast_events(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, uint32_t S, uint32_t E,
-                           uint32_t Sprev, int& lastS) {
+                           uint32_t kill, int& lastS) {
     const int cut = (stream == STREAM_S) ? cfg.cutS : cfg.cutA;
     const int p0 = 32 * it.w;
-    if (E != 0u && it.emit_on) {
-        // cheap exact pre-filter: a component spanning ts..t has length t - ts - 1; kill the E bits whose S bit is
-        // only 9..12 positions back when that is below the cutoff
-        uint32_t kill = 0u;
-        if (cut >= 9) kill |= fsl(Sprev, S, 9);
-        if (cut >= 10) kill |= fsl(Sprev, S, 10);
-        if (cut >= 11) kill |= fsl(Sprev, S, 11);
-        if (cut >= 12) kill |= fsl(Sprev, S, 12);
-        uint32_t x = E & ~kill, kept = 0u;
-        while (x) {
-            const int i = ctz32(x);
-            x &= x - 1u;
-            const uint32_t sb = S & lowmask(i);
-            const int ts = sb ? p0 + 31 - clz32(sb) : lastS;
-            const int ls = ts - 7, le = p0 + i - 8;
-            if (le - ls >= cut) {
-                sk.rec(stream, ls, le, cfg.s, 0, (i << 18) | (cfg.s << 2));
-                kept |= 1u << i;
-            }
+    uint32_t x = E & ~kill, kept = 0u;
+    while (x) {  // exact check of the survivors
+        const int i = ctz32(x);
+        x &= x - 1u;
+        const uint32_t sb = S & lowmask(i);
+        const int ts = sb ? p0 + 31 - clz32(sb) : lastS;
+        const int ls = ts - 7, le = p0 + i - 8;
+        if (le - ls >= cut) {
+            sk.rec(stream, ls, le, cfg.s, 0, (i << 18) | (cfg.s << 2));
+            kept |= 1u << i;
         }
-        const uint32_t el = E & ~kept;
-        if (el) sk.dropped(stream, 31 - clz32(el));
     }
+    const uint32_t el = E & ~kept;
+    if (el) sk.dropped(stream, 31 - clz32(el));
     if (S) lastS = p0 + 31 - clz32(S);
 }
 
@@ -333,31 +400,26 @@ RB_HD void win_to_fast(const WinState& st, int& lastS) {
 
 template <class Sink>
 RB_HD void perfect_fast(Sink& sk, const IterCtx& it, const LaneCfg& cfg, uint32_t g, int& pst) {
-    uint32_t r = g;
     const int p0 = 32 * it.w;
-    if (pst >= 0) {
-        const int lead = ctz32(~r);
-        if (lead >= 32) return;
-        const int end = p0 + lead;
-        if (end - pst >= cfg.cutP) emit_perfect(sk, it, cfg, pst, end, end);
-        pst = -1;
-        r &= ~lowmask(lead);
-    }
-    const int trail = clz32(~r);
-    if (trail > 0) {
-        pst = p0 + 32 - trail;
-        r &= lowmask(32 - trail);
-    }
-    if (cfg.cutP > 30 || r == 0u) return;
+    const int lead = ctz32(~g), trail = clz32(~g);
+    const bool has = pst >= 0, whole = g == 0xFFFFFFFFu;
+    // the open run (if any) ends at bit `lead`; the other runs strictly inside the word can only reach cutoffs <= 30
+    uint32_t r = has ? (g & ~lowmask(lead)) : g;
+    r &= lowmask(32 - trail);
     const uint32_t e2 = r & (r >> 1), e4 = e2 & (e2 >> 2);
     const uint32_t pre = (cfg.cutP >= 8) ? (e4 & (e4 >> 4)) : (e4 & (e2 >> 4));  // runs >= 8 / >= 6
-    if (pre == 0u) return;
-    while (r) {  // rare: some interior run may reach the cutoff
-        const int a = ctz32(r);
-        const int len = ctz32(~(r >> a));
-        if (len >= cfg.cutP) emit_perfect(sk, it, cfg, p0 + a, p0 + a + len, p0 + a + len);
-        r &= ~(lowmask(len) << a);
+    const bool ends = has && !whole && (p0 + lead - pst >= cfg.cutP);
+    if (ends || (pre != 0u && cfg.cutP <= 30)) {  // rare
+        if (ends) emit_perfect(sk, it, cfg, pst, p0 + lead, p0 + lead);
+        if (cfg.cutP <= 30)
+            while (r) {
+                const int a = ctz32(r);
+                const int len = ctz32(~(r >> a));
+                if (len >= cfg.cutP) emit_perfect(sk, it, cfg, p0 + a, p0 + a + len, p0 + a + len);
+                r &= ~(lowmask(len) << a);
+            }
     }
+    pst = whole ? (has ? pst : p0) : (trail > 0 ? p0 + 32 - trail : -1);
 }
 
 // ---- slow word: the reference state machines bit by bit ----------------------------------------------------------
@@ -437,13 +499,34 @@ RB_HD void win_tail(Sink& sk, const LaneCfg& cfg, int stream, int L, const WinSt
 // Phase 1: bring X_s[w+1] in and compute the anchor word A_s[w]. Returns A_s[w] (0 for idle lanes).
 RB_HD uint32_t lane_phase1(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
     if (cfg.s == 0) return 0u;
-    st.x_nxt = x_word(cw, w + 1, cfg.s);
+    st.x_nxt = x_word_cached(cw, w + 1, cfg.s, st.xc);
     const uint32_t xa = st.x_cur | anchor_endmask(w, L, cfg.s);
     const uint32_t xan = st.x_nxt | anchor_endmask(w + 1, L, cfg.s);
     // a zero was seen: run lengths are exact from here on; a run already >= 2s long can never be an anchor,
     // whatever its true length
     if (xa != 0xFFFFFFFFu || st.lenL >= 2 * cfg.s) st.sync |= SYNC_X;
     return anchor_word(cw, w, L, cfg.s, xa, xan, st.lenL);
+}
+
+// Phase 1 for emitting words (warm-up bookkeeping not needed). Common case in straight-line code: no run touching
+// this word can reach 2s positions and the word is not near the contig end; then A_s[w] = the positions of X_s that
+// lie in a run of at least 3 (anchor_size, parse_anchored_shiftxor.cpp:44). Everything else takes anchor_word.
+RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
+    if (cfg.s == 0) return 0u;
+    st.x_nxt = x_word_cached(cw, w + 1, cfg.s, st.xc);
+    const uint32_t x = st.x_cur, xn = st.x_nxt, xp = st.x_prev;
+    const int K2 = 2 * cfg.s;
+    const int lead = ctz32(~x), trail = clz32(~x), leadn = ctz32(~xn);
+    const bool rare = (w + 1 >= cfg.wm) | (K2 <= 30) | (st.lenL + lead >= K2) | (trail + leadn >= K2) | (lead == 32) |
+                      (leadn == 32);
+    if (rare) {
+        const uint32_t xa = x | anchor_endmask(w, L, cfg.s);
+        const uint32_t xan = xn | anchor_endmask(w + 1, L, cfg.s);
+        return anchor_word(cw, w, L, cfg.s, xa, xan, st.lenL);
+    }
+    const uint32_t l1 = fsl(xp, x, 1), l2 = fsl(xp, x, 2), r1 = fsr(x, xn, 1), r2 = fsr(x, xn, 2);
+    st.lenL = trail;
+    return x & ((l1 & (l2 | r1)) | (r1 & r2));
 }
 
 // Phase 2: B_m[w] from the neighbouring anchors, window tests, seed machines, state rotation.
@@ -459,6 +542,7 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
         uint32_t sS, eS, sSp, sA, eA, sAp;
         ev_step(passS, st.es, sS, eS, sSp);
         ev_step(passA, st.ea, sA, eA, sAp);
+        const uint32_t killA = smear_step(cfg, st, sA, sAp);
         if (machines_on) {
             if (!it.slow) {
                 if (it.prev_slow) {
@@ -466,8 +550,9 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
                     win_to_fast(st.A, st.ea.lastS);
                 }
                 perfect_fast(sk, it, cfg, x, st.pst);
-                win_fast_events(sk, it, cfg, STREAM_S, sS, eS, sSp, st.es.lastS);
-                win_fast_events(sk, it, cfg, STREAM_A, sA, eA, sAp, st.ea.lastS);
+                if (eS | sS) win_fast_events(sk, it, cfg, STREAM_S, sS, eS, 0u, st.es.lastS);
+                // the smear looks back up to three words: trust it once four fast words in a row were seen
+                if (eA | sA) win_fast_events(sk, it, cfg, STREAM_A, sA, eA, it.fastrun >= 4 ? killA : 0u, st.ea.lastS);
             } else {
                 const uint32_t prev_v31 = cw[it.w - 1].v >> 31;
                 const int p0 = 32 * it.w;
@@ -526,6 +611,8 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
     st.es.P = st.es.S = 0u;
     st.es.lastS = -1;
     st.ea = st.es;
+    for (int i = 0; i < 7; ++i) st.sm[i] = 0u;
+    st.xc.h = st.xc.l = 0u; st.xc.idx = -0x40000000;
     st.sync = (q == 0) ? SYNC_ALL : 0;
     st.zS = st.zA = 0;
     if (cfg.s == 0) return;

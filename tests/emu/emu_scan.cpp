@@ -87,7 +87,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
             ItemOut& io = items[ci * lay.nbands + band];
             LaneCfg cfg[32];
             LaneState st[32];
-            for (int j = 0; j < lay.bw; ++j) cfg[j] = band_lane_cfg(lay, band, j);
+            for (int j = 0; j < lay.bw; ++j) { cfg[j] = band_lane_cfg(lay, band, j); lane_cfg_set_contig(cfg[j], (int)L); }
             int H = warm0;
             int we = ch.w0;  // first emitting word of the current warm-up (moves on a fast -> slow transition)
             int nb = we;     // first word of the run of full-N words that ends right before it
@@ -97,7 +97,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                 const int Ha = warmup_anchor_words(q, H);
                 for (int j = 0; j < lay.bw; ++j) lane_init(cfg[j], st[j], cw, q);
                 bool restart = false, replay = false;
-                int prev_slow = 1;
+                int prev_slow = 1, fastrun = 0;
                 for (int w = q; w < ch.w1 && !restart;) {
                     if (w >= q + Ha && w < we - 2) {  // warming up inside an N run: jump
                         int r = 0;
@@ -118,13 +118,15 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                         break;
                     }
                     uint32_t a[32 + 4] = {0};
-                    for (int j = 0; j < lay.bw; ++j) a[j + 2] = lane_phase1(cfg[j], st[j], cw, w, (int)L);
+                    for (int j = 0; j < lay.bw; ++j)
+                        a[j + 2] = slow ? lane_phase1(cfg[j], st[j], cw, w, (int)L) : lane_phase1_fast(cfg[j], st[j], cw, w, (int)L);
+                    fastrun = slow ? 0 : std::min(fastrun + 1, 4);
                     if (q > 0 && w == q + Ha - 2)
                         for (int j = 0; j < lay.bw; ++j) if (cfg[j].s && !(st[j].sync & SYNC_X)) restart = true;
                     if (q > 0 && w == we)
                         for (int j = 0; j < lay.bw; ++j) if (cfg[j].motif && (st[j].sync & SYNC_ALL) != SYNC_ALL) restart = true;
                     if (restart) break;
-                    IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow;
+                    IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
                     EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
                     const uint32_t off = (uint32_t)io.raw.size();
                     for (int j = 0; j < lay.bw; ++j)
