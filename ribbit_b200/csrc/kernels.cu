@@ -153,7 +153,27 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
     }
 
     const int guard = b.lay.guard;
-    while (__any_sync(0xFFFFFFFFu, active)) {
+    for (;;) {
+        // ---- end of the chunk: tail flush (last chunk of a contig), record count -------------------------------
+        if (active && w >= ch.w1) {
+            if (ch.last) {
+                sk.counts = 0u;
+                lane_tail(sk, cfg, st, L);
+                const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
+                if (j == 0) meta[ch.w1] = make_meta(counts, 0, 0, 1, off);
+            }
+            __syncwarp(gmask);
+            if (j == 0) {
+                const int n = *cnt;
+                b.item_count[item] = n;
+                if (n > sk.cap) atomicAdd(b.counters + 0, 1);
+                if (restarts) atomicAdd(b.counters + 1, restarts);
+            }
+            active = false;
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+
+        // ---- general path: one word (warm-up, slow words, restarts, N-run jumps) --------------------------------
         const bool can = active && w >= q + Ha && w < we - 2;
         if (__any_sync(0xFFFFFFFFu, can)) {
             // warming up inside an N run: jump over words whose neighbourhood is all N (scan_core.h, lane_skip)
@@ -218,21 +238,34 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             }
             prev_slow = slow;
             ++w;
-            if (w >= ch.w1) {
-                if (ch.last) {
-                    sk.counts = 0u;
-                    lane_tail(sk, cfg, st, L);
-                    const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
-                    if (j == 0) meta[ch.w1] = make_meta(counts, 0, 0, 1, off);
+        }
+
+        // ---- tight path: consecutive fast, emitting words of a whole-warp item ---------------------------------
+        if constexpr (BW == 32) {
+            if (active && !badmask && w >= we) {
+                uint32_t vprev = cw[w - 1].v;
+                while (w < ch.w1) {
+                    const uint32_t vcur = cw[w].v;
+                    if ((vprev & vcur) != 0xFFFFFFFFu || w == cg.nw - 1 || prev_slow) break;
+                    vprev = vcur;
+                    const uint32_t af = lane_phase1_fast(cfg, st, cw, w, L);
+                    uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
+                    uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
+                    if (j < 2) f_m2 = 0u;
+                    if (j < 1) f_m1 = 0u;
+                    if (j + 1 >= BW) f_p1 = 0u;
+                    if (j + 2 >= BW) f_p2 = 0u;
+                    fastrun = min(fastrun + 1, 4);
+                    IterCtx it;
+                    it.w = w; it.L = L; it.emit_on = 1; it.slow = 0; it.prev_slow = 0; it.fastrun = fastrun;
+                    sk.counts = 0u; sk.dS = 0; sk.dA = 0;
+                    lane_phase2_fast(sk, cfg, st, it, f_m2, f_m1, f_p1, f_p2);
+                    const uint32_t counts = __reduce_add_sync(0xFFFFFFFFu, sk.counts);
+                    const int dS = __reduce_max_sync(0xFFFFFFFFu, sk.dS), dA = __reduce_max_sync(0xFFFFFFFFu, sk.dA);
+                    if (j == 0) meta[w] = make_meta(counts, dS, dA, 0, off);
+                    off += (counts & 0x3FFu) + ((counts >> 10) & 0x3FFu) + (counts >> 20);
+                    ++w;
                 }
-                __syncwarp(gmask);
-                if (j == 0) {
-                    const int n = *cnt;
-                    b.item_count[item] = n;
-                    if (n > sk.cap) atomicAdd(b.counters + 0, 1);
-                    if (restarts) atomicAdd(b.counters + 1, restarts);
-                }
-                active = false;
             }
         }
     }

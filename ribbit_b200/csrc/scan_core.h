@@ -529,10 +529,41 @@ RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWo
     return x & ((l1 & (l2 | r1)) | (r1 & r2));
 }
 
+// Phase 2 of a fast, emitting word (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so
+// o.v is all ones and the N plane is not consulted.
+template <class Sink>
+RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const IterCtx& it, uint32_t a_m2, uint32_t a_m1,
+                            uint32_t a_p1, uint32_t a_p2) {
+    if (cfg.motif) {
+        const uint32_t x = st.x_cur;
+        const uint32_t b = x | a_m2 | a_m1 | a_p1 | a_p2;
+        const uint32_t passS = ~fail_ge2(x, st.cs);
+        const uint32_t passA = ~fail_ge3(b, st.ca);
+        uint32_t sS, eS, sSp, sA, eA, sAp;
+        ev_step(passS, st.es, sS, eS, sSp);
+        ev_step(passA, st.ea, sA, eA, sAp);
+        const uint32_t killA = smear_step(cfg, st, sA, sAp);
+        if (it.prev_slow) {
+            win_to_fast(st.S, st.es.lastS);
+            win_to_fast(st.A, st.ea.lastS);
+        }
+        perfect_fast(sk, it, cfg, x, st.pst);
+        if (eS | sS) win_fast_events(sk, it, cfg, STREAM_S, sS, eS, 0u, st.es.lastS);
+        // the smear looks back up to three words: trust it once four fast words in a row were seen
+        if (eA | sA) win_fast_events(sk, it, cfg, STREAM_A, sA, eA, it.fastrun >= 4 ? killA : 0u, st.ea.lastS);
+    }
+    st.x_prev = st.x_cur;
+    st.x_cur = st.x_nxt;
+}
+
 // Phase 2: B_m[w] from the neighbouring anchors, window tests, seed machines, state rotation.
 template <class Sink>
 RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, const IterCtx& it,
                        uint32_t a_m2, uint32_t a_m1, uint32_t a_p1, uint32_t a_p2, int machines_on) {
+    if (!it.slow && machines_on) {
+        lane_phase2_fast(sk, cfg, st, it, a_m2, a_m1, a_p1, a_p2);
+        return;
+    }
     if (cfg.motif) {
         const PlaneWord o = cw[it.w];
         const uint32_t x = st.x_cur;
@@ -542,18 +573,9 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
         uint32_t sS, eS, sSp, sA, eA, sAp;
         ev_step(passS, st.es, sS, eS, sSp);
         ev_step(passA, st.ea, sA, eA, sAp);
-        const uint32_t killA = smear_step(cfg, st, sA, sAp);
+        (void)smear_step(cfg, st, sA, sAp);
         if (machines_on) {
-            if (!it.slow) {
-                if (it.prev_slow) {
-                    win_to_fast(st.S, st.es.lastS);
-                    win_to_fast(st.A, st.ea.lastS);
-                }
-                perfect_fast(sk, it, cfg, x, st.pst);
-                if (eS | sS) win_fast_events(sk, it, cfg, STREAM_S, sS, eS, 0u, st.es.lastS);
-                // the smear looks back up to three words: trust it once four fast words in a row were seen
-                if (eA | sA) win_fast_events(sk, it, cfg, STREAM_A, sA, eA, it.fastrun >= 4 ? killA : 0u, st.ea.lastS);
-            } else {
+            {
                 const uint32_t prev_v31 = cw[it.w - 1].v >> 31;
                 const int p0 = 32 * it.w;
                 int pv = (int)prev_v31;
