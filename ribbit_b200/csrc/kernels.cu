@@ -84,6 +84,10 @@ struct GpuSink {
     __device__ __forceinline__ void dropped(int stream, int tw) {
         if (stream == STREAM_S) dS = max(dS, tw + 1); else dA = max(dA, tw + 1);
     }
+    __device__ __forceinline__ void dropped_mask(int stream, uint32_t el) {
+        const int d = 32 - __clz((int)el);  // 0 when nothing was elided
+        if (stream == STREAM_S) dS = max(dS, d); else dA = max(dA, d);
+    }
 };
 
 static const int SCAN_WARPS = 4;

@@ -387,9 +387,8 @@ RB_HD void win_fast_events(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int 
             kept |= 1u << i;
         }
     }
-    const uint32_t el = E & ~kept;
-    if (el) sk.dropped(stream, 31 - clz32(el));
-    if (S) lastS = p0 + 31 - clz32(S);
+    sk.dropped_mask(stream, E & ~kept);
+    lastS = S ? p0 + 31 - clz32(S) : lastS;
 }
 
 // lastS of the bit-parallel view from the reference machine's state (slow word -> fast word)
@@ -516,17 +515,28 @@ RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWo
     st.x_nxt = x_word_cached(cw, w + 1, cfg.s, st.xc);
     const uint32_t x = st.x_cur, xn = st.x_nxt, xp = st.x_prev;
     const int K2 = 2 * cfg.s;
-    const int lead = ctz32(~x), trail = clz32(~x), leadn = ctz32(~xn);
-    const bool rare = (w + 1 >= cfg.wm) | (K2 <= 30) | (st.lenL + lead >= K2) | (trail + leadn >= K2) | (lead == 32) |
-                      (leadn == 32);
-    if (rare) {
+    if ((w + 1 >= cfg.wm) | (x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu)) {  // rare: whole words of ones, contig end
         const uint32_t xa = x | anchor_endmask(w, L, cfg.s);
         const uint32_t xan = xn | anchor_endmask(w + 1, L, cfg.s);
         return anchor_word(cw, w, L, cfg.s, xa, xan, st.lenL);
     }
+    const int lead = ctz32(~x), trail = clz32(~x), leadn = ctz32(~xn);
     const uint32_t l1 = fsl(xp, x, 1), l2 = fsl(xp, x, 2), r1 = fsr(x, xn, 1), r2 = fsr(x, xn, 2);
+    uint32_t a = x & ((l1 & (l2 | r1)) | (r1 & r2));
+    // runs that touch a word edge: their full length is known from the neighbours
+    a &= (st.lenL + lead >= K2) ? ~lowmask(lead) : 0xFFFFFFFFu;
+    a &= (trail + leadn >= K2) ? lowmask(32 - trail) : 0xFFFFFFFFu;
+    if (K2 <= 30) {  // small shifts: a run inside the word can be too long as well
+        uint32_t e = x;
+        for (int k = 1; k < K2;) { const int sh = (k < K2 - k) ? k : K2 - k; e &= e >> sh; k += sh; }
+        if (e) {
+            uint32_t d = e;
+            for (int k = 1; k < K2;) { const int sh = (k < K2 - k) ? k : K2 - k; d |= d << sh; k += sh; }
+            a &= ~d;
+        }
+    }
     st.lenL = trail;
-    return x & ((l1 & (l2 | r1)) | (r1 & r2));
+    return a;
 }
 
 // Phase 2 of a fast, emitting word (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so

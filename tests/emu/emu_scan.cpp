@@ -29,6 +29,7 @@ struct EmuSink {
         counts += 1u << (10 * stream);
     }
     void dropped(int stream, int tw) { if (tw + 1 > dmax[stream]) dmax[stream] = tw + 1; }
+    void dropped_mask(int stream, uint32_t el) { if (el) dropped(stream, 31 - clz32(el)); }
 };
 
 void pack(const char* seq, int64_t L, int guard, std::vector<PlaneWord>& pw) {
