@@ -213,6 +213,7 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.n_buckets = c->bucket_base[n];
     b.n_plane_words = c->plane_start[n];
     b.warm0 = WARMUP_WORDS;
+    b.debug = c->params.reserved;
     b.n_merge_blocks = (int)((b.n_buckets + MERGE_BLOCK - 1) / MERGE_BLOCK);
     if ((rc = ensure(c, c->d_planes, (size_t)b.n_plane_words * sizeof(PlaneWord)))) return rc;
     if ((rc = ensure(c, c->d_meta, (size_t)b.n_buckets * c->lay.nbands * sizeof(Meta)))) return rc;
@@ -247,7 +248,7 @@ const char* rb_last_error(const rb_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 
 rb_ctx* rb_create(int device, const rb_params* params) {
     if (!params || params->min_mlen < 1 || params->max_mlen < params->min_mlen || params->max_mlen > 1000 ||
-        params->max_mlen - params->min_mlen + 1 > 224 || params->reserved != 0 || params->chunk_words < 0) {
+        params->max_mlen - params->min_mlen + 1 > 224 || params->reserved < 0 || params->reserved > 3 || params->chunk_words < 0) {
         fail(nullptr, RB_E_ARG, "rb_create: bad parameters (need 1 <= min_mlen <= max_mlen <= 1000, at most 224 motif sizes)");
         return nullptr;
     }

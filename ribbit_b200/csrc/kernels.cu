@@ -136,9 +136,28 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             }
         }
     }
+    // a chunk that lies strictly inside an N run (the word before it and all its words are N) emits nothing:
+    // no window is evaluated and every run was closed by the first N of the run
+    {
+        bool alln = active && nb < ch.w0 && !ch.last && !(b.debug & 2);
+        for (int base = 0; __any_sync(0xFFFFFFFFu, alln && ch.w0 + base < ch.w1); base += BW) {  // warp-uniform trip count
+            const int wq = ch.w0 + base + j;
+            const bool f = !alln || wq >= ch.w1 || full_n(cw, wq);
+            const unsigned bits = __ballot_sync(0xFFFFFFFFu, f) & gmask;
+            if (bits != gmask) alln = false;
+        }
+        if (alln) {
+            for (int wq = ch.w0 + j; wq < ch.w1; wq += BW) meta[wq] = make_meta(0u, 0, 0, 1, off0);
+            if (j == 0) b.item_count[item] = 0;
+            active = false;
+        }
+    }
+    const int nb0 = nb;
     LaneState st;
     int H = b.warm0;
-    int we = ch.w0;  // first emitting word of the current warm-up (moves on a fast -> slow transition)
+    const int e0 = ch.w0;  // first emitting word
+    int we = e0;           // word at which the lane state must be complete (end of the current warm-up)
+    int force = 0;         // the warm-up rebuilds the reference machines: process its words bit-serially
     int q = warmup_start(we, nb, H);
     int Ha = warmup_anchor_words(q, H);
     lane_init(cfg, st, cw, q);
@@ -178,7 +197,16 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
         if (!__any_sync(0xFFFFFFFFu, active)) break;
 
         // ---- general path: one word (warm-up, slow words, restarts, N-run jumps) --------------------------------
-        const bool can = active && w >= q + Ha && w < we - 2;
+        const int lim = max(we, e0) - 2;  // no word is emitted before max(we, e0)
+        if (active && w >= q + Ha && w - 1 >= nb0) {
+            // inside the N run that ends right before the chunk (words nb0 .. e0-1 are all N): one jump
+            const int k = min(e0 - guard, lim) - w;
+            if (k > 0) {
+                w += k;
+                lane_skip(cfg, st, cw, w, k);
+            }
+        }
+        const bool can = active && w >= q + Ha && w < lim;
         if (__any_sync(0xFFFFFFFFu, can)) {
             // warming up inside an N run: jump over words whose neighbourhood is all N (scan_core.h, lane_skip)
             const int wq = w - 1 + j;
@@ -186,16 +214,16 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             const unsigned bits = (__ballot_sync(0xFFFFFFFFu, f) & gmask) >> (g * BW);
             const unsigned inv = ~bits & (BW == 32 ? 0xFFFFFFFFu : ((1u << BW) - 1u));
             const int r = inv ? __ffs((int)inv) - 1 : BW;
-            const int k = can ? min(r - guard - 1, we - 2 - w) : 0;
+            const int k = can ? min(r - guard - 1, lim - w) : 0;
             if (k > 0) {
                 w += k;
                 lane_skip(cfg, st, cw, w, k);
             }
         }
-        int slow = active ? ((w < we) || !word_is_fast(cw, w, cg.nw)) : 1;
+        int slow = active ? ((force && w < we) || !word_is_fast(cw, w, cg.nw)) : 1;
         if (active && slow && !prev_slow) {
             // fast -> slow: the reference machines' state is rebuilt by a warm-up that ends here
-            we = w; nb = w; H = b.warm0;
+            we = w; nb = w; H = b.warm0; force = 1;
             q = warmup_start(we, nb, H);
             Ha = warmup_anchor_words(q, H);
             lane_init(cfg, st, cw, q);
@@ -231,7 +259,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
             ++restarts;
         } else if (active) {
             IterCtx it;
-            it.w = w; it.L = L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
+            it.w = w; it.L = L; it.emit_on = w >= we && w >= e0; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
             sk.counts = 0u; sk.dS = 0; sk.dA = 0;
             lane_phase2(sk, cfg, st, cw, it, a_m2, a_m1, a_p1, a_p2, w >= q + Ha);
             if (it.emit_on) {
@@ -246,7 +274,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
 
         // ---- tight path: consecutive fast, emitting words of a whole-warp item ---------------------------------
         if constexpr (BW == 32) {
-            if (active && !badmask && w >= we) {
+            if (active && !badmask && w > we && w >= e0 && !(b.debug & 1)) {  // word `we` (state check) goes through the general path
                 uint32_t vprev = cw[w - 1].v;
                 while (w < ch.w1) {
                     const uint32_t vcur = cw[w].v;

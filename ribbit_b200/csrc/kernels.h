@@ -24,6 +24,7 @@ struct DevBatch {
     long long n_buckets;      // sum over contigs of nw + 1
     long long n_plane_words;  // plane words including guard words
     int warm0;
+    int debug;                // bit 0: no tight loop, bit 1: no all-N chunk skip (diagnostics)
 
     const uint8_t* ascii;
     const Contig* contigs;          // [n_contigs]

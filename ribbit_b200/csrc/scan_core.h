@@ -375,7 +375,7 @@ RB_HD void win_fast_events(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int 
                            uint32_t kill, int& lastS) {
     const int cut = (stream == STREAM_S) ? cfg.cutS : cfg.cutA;
     const int p0 = 32 * it.w;
-    uint32_t x = E & ~kill, kept = 0u;
+    uint32_t x = it.emit_on ? (E & ~kill) : 0u, kept = 0u;
     while (x) {  // exact check of the survivors
         const int i = ctz32(x);
         x &= x - 1u;
@@ -518,8 +518,10 @@ RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWo
     if ((w + 1 >= cfg.wm) | (x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu)) {  // rare: whole words of ones, contig end
         const uint32_t xa = x | anchor_endmask(w, L, cfg.s);
         const uint32_t xan = xn | anchor_endmask(w + 1, L, cfg.s);
+        if (xa != 0xFFFFFFFFu || st.lenL >= K2) st.sync |= SYNC_X;
         return anchor_word(cw, w, L, cfg.s, xa, xan, st.lenL);
     }
+    st.sync |= SYNC_X;  // this word holds a mismatch: run lengths are exact from here on
     const int lead = ctz32(~x), trail = clz32(~x), leadn = ctz32(~xn);
     const uint32_t l1 = fsl(xp, x, 1), l2 = fsl(xp, x, 2), r1 = fsr(x, xn, 1), r2 = fsr(x, xn, 2);
     uint32_t a = x & ((l1 & (l2 | r1)) | (r1 & r2));
@@ -539,7 +541,21 @@ RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWo
     return a;
 }
 
-// Phase 2 of a fast, emitting word (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so
+// nz = failing windows of this word; zrun = failing windows at the end of the previous words (saturating).
+// Returns 1 if nine consecutive failing windows were seen.
+RB_HD int nine_fails(uint32_t nz, int& zrun) {
+    const int lead = ctz32(~nz);
+    uint32_t e = nz & (nz >> 1);
+    e &= e >> 2;
+    e &= e >> 4;
+    e &= nz >> 8;
+    const int hit = (e != 0u) || (zrun + lead >= 9);
+    const int tr = clz32(~nz);
+    zrun = (tr == 32) ? ((zrun + 32 > 64) ? 64 : zrun + 32) : tr;
+    return hit;
+}
+
+// Phase 2 of a fast word (it.slow == 0, machines on) (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so
 // o.v is all ones and the N plane is not consulted.
 template <class Sink>
 RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const IterCtx& it, uint32_t a_m2, uint32_t a_m1,
@@ -556,6 +572,13 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const I
         if (it.prev_slow) {
             win_to_fast(st.S, st.es.lastS);
             win_to_fast(st.A, st.ea.lastS);
+        }
+        if (!it.emit_on) {
+            // warm-up in fast words: pst is exact once a mismatch was seen; lastS once a component start was seen
+            // or nine windows in a row failed (any later component starts inside the scanned range)
+            if (x != 0xFFFFFFFFu) st.sync |= SYNC_P;
+            if (sS != 0u || nine_fails(~passS, st.zS)) st.sync |= SYNC_S;
+            if (sA != 0u || nine_fails(~passA, st.zA)) st.sync |= SYNC_A;
         }
         perfect_fast(sk, it, cfg, x, st.pst);
         if (eS | sS) win_fast_events(sk, it, cfg, STREAM_S, sS, eS, 0u, st.es.lastS);
@@ -639,7 +662,8 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
     st.pst = -1;
     st.S.cur = st.S.ls = st.S.le = -1;
     st.A = st.S;
-    st.es.F = st.es.r2 = st.es.r4 = st.es.r8 = 0xFFFFFFFFu;  // nothing before the contig start: "failing" windows
+    // nothing before the contig start: "failing" windows; a cold start must not invent a run of failing windows
+    st.es.F = st.es.r2 = st.es.r4 = st.es.r8 = (q == 0) ? 0xFFFFFFFFu : 0u;
     st.es.P = st.es.S = 0u;
     st.es.lastS = -1;
     st.ea = st.es;

@@ -96,9 +96,9 @@ def load_library(path=LIB_PATH):
 class Scanner:
     """One scan context on one GPU (rb_ctx). Motif range = ribbit's -m / -M."""
 
-    def __init__(self, min_mlen=2, max_mlen=100, device=0, chunk_words=0):
+    def __init__(self, min_mlen=2, max_mlen=100, device=0, chunk_words=0, debug=0):
         self.lib = load_library()
-        p = RbParams(min_mlen, max_mlen, chunk_words, 0)
+        p = RbParams(min_mlen, max_mlen, chunk_words, debug)
         self.ctx = self.lib.rb_create(device, ctypes.byref(p))
         if not self.ctx:
             raise RibbitScanError(self.lib.rb_last_error(None).decode())

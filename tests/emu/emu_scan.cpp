@@ -90,9 +90,12 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
             LaneState st[32];
             for (int j = 0; j < lay.bw; ++j) { cfg[j] = band_lane_cfg(lay, band, j); lane_cfg_set_contig(cfg[j], (int)L); }
             int H = warm0;
-            int we = ch.w0;  // first emitting word of the current warm-up (moves on a fast -> slow transition)
-            int nb = we;     // first word of the run of full-N words that ends right before it
+            const int e0 = ch.w0;  // first emitting word
+            int we = e0;           // word at which the lane state must be complete (end of the current warm-up)
+            int force = 0;         // the warm-up rebuilds the reference machines: process its words bit-serially
+            int nb = we;           // first word of the run of full-N words that ends right before it
             while (nb > 0 && full_n(cw, nb - 1)) --nb;
+            const int nb0 = nb;
             for (;;) {
                 const int q = warmup_start(we, nb, H);
                 const int Ha = warmup_anchor_words(q, H);
@@ -100,10 +103,10 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                 bool restart = false, replay = false;
                 int prev_slow = 1, fastrun = 0;
                 for (int w = q; w < ch.w1 && !restart;) {
-                    if (w >= q + Ha && w < we - 2) {  // warming up inside an N run: jump
-                        int r = 0;
-                        while (r < lay.bw && w - 1 + r < nw + lay.guard && full_n(cw, w - 1 + r)) ++r;
-                        const int k = std::min(r - lay.guard - 1, we - 2 - w);
+                    const int lim = std::max(we, e0) - 2;  // no word is emitted before max(we, e0)
+                    if (w >= q + Ha && w - 1 >= nb0) {
+                        // inside the N run that ends right before the chunk (words nb0 .. e0-1 are all N): one jump
+                        const int k = std::min(e0 - lay.guard, lim) - w;
                         if (k > 0) {
                             w += k;
                             for (int j = 0; j < lay.bw; ++j) lane_skip(cfg[j], st[j], cw, w, k);
@@ -111,10 +114,21 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                             continue;
                         }
                     }
-                    const int slow = (w < we) || !word_is_fast(cw, w, nw);
+                    if (w >= q + Ha && w < lim) {  // warming up inside an N run: jump
+                        int r = 0;
+                        while (r < lay.bw && w - 1 + r < nw + lay.guard && full_n(cw, w - 1 + r)) ++r;
+                        const int k = std::min(r - lay.guard - 1, lim - w);
+                        if (k > 0) {
+                            w += k;
+                            for (int j = 0; j < lay.bw; ++j) lane_skip(cfg[j], st[j], cw, w, k);
+                            if (skips) ++*skips;
+                            continue;
+                        }
+                    }
+                    const int slow = (force && w < we) || !word_is_fast(cw, w, nw);
                     if (slow && !prev_slow) {
                         // fast -> slow: the reference machines' state is rebuilt by a warm-up that ends here
-                        we = w; nb = w; H = warm0; replay = true;
+                        we = w; nb = w; H = warm0; force = 1; replay = true;
                         if (replays) ++*replays;
                         break;
                     }
@@ -127,7 +141,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                     if (q > 0 && w == we)
                         for (int j = 0; j < lay.bw; ++j) if (cfg[j].motif && (st[j].sync & SYNC_ALL) != SYNC_ALL) restart = true;
                     if (restart) break;
-                    IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= we; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
+                    IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= we && w >= e0; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
                     EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
                     const uint32_t off = (uint32_t)io.raw.size();
                     for (int j = 0; j < lay.bw; ++j)

@@ -24,5 +24,6 @@ c = synth.random_bases(rng, L).tobytes()
 run("c2 with N runs", a)
 run("c2 without N runs", b)
 run("pure random", c)
-for cw in (128, 256, 1024, 4096):
+for cw in (64, 128, 256, 512, 1024):
     run("c2 without N runs", b, cw)
+    run("c2 with N runs", a, cw)
