@@ -93,7 +93,7 @@ struct GpuSink {
 static const int SCAN_WARPS = 4;
 
 template <int BW>
-__global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(DevBatch b) {
+__global__ void __launch_bounds__(SCAN_WARPS * 32, 5) scan_kernel(DevBatch b) {
     constexpr int GROUPS = 32 / BW;
     __shared__ int s_cnt[SCAN_WARPS][GROUPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

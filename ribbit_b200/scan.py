@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libribbit_scan.so")
+LIB_PATH = os.environ.get("RIBBIT_SCAN_LIB", os.path.join(_HERE, "lib", "libribbit_scan.so"))  # override: experiments only
 
 REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("mlen", "<u2"), ("flags", "<u2"), ("time", "<i4")])
 REC_DROPPED, REC_PSEUDO, REC_NOCOMMIT = 1, 2, 4
