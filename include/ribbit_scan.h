@@ -142,6 +142,12 @@ typedef struct rb_seedinfo {
 } rb_seedinfo;
 int rb_filter_seeds(rb_ctx *ctx, const rb_seed *seeds, int64_t n, rb_seedinfo *out);
 
+/* Anchor planes A_s (generateAnchoredShiftXORs, parse_anchored_shiftxor.cpp:20-56: runs of 1s of the match plane X_s
+ * with 3 <= length < 2s that are closed inside the scanned range) of contig c for shifts shift_lo..shift_hi, computed on
+ * the device: out[(s - shift_lo) * ceil(L/32) + w], bit i of word w = position 32*w+i. The host side of the reference
+ * (order-dependent merges, per-seed stage) reads B_m = X_m | A_{m-2} | A_{m-1} | A_{m+1} | A_{m+2} (fasta_utils.cpp:143-161). */
+int rb_get_anchor_planes(rb_ctx *ctx, int32_t contig, int32_t shift_lo, int32_t shift_hi, uint32_t *out);
+
 /* Copies the packed planes of contig c to host arrays of ceil(L/32) words (bit i of word w = position 32*w+i):
  * hi/lo = the two code bits (A=00 C=01 G=10 T=11), nn = N plane. Any pointer may be NULL. */
 int rb_get_planes(rb_ctx *ctx, int32_t contig, uint32_t *hi, uint32_t *lo, uint32_t *nn);

@@ -443,6 +443,25 @@ int rb_get_planes(rb_ctx* c, int32_t contig, uint32_t* hi, uint32_t* lo, uint32_
     return RB_OK;
 }
 
+int rb_get_anchor_planes(rb_ctx* c, int32_t contig, int32_t shift_lo, int32_t shift_hi, uint32_t* out) {
+    if (!c || !out) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_get_anchor_planes: planes exist after rb_scan_device");
+    if (contig < 0 || contig >= c->batch.n_contigs) return fail(c, RB_E_ARG, "rb_get_anchor_planes: contig out of range");
+    if (shift_lo < 1 || shift_hi < shift_lo || shift_hi > c->lay.s_hi) return fail(c, RB_E_ARG, "rb_get_anchor_planes: shifts out of range");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    const Contig& cg = c->contigs[contig];
+    const int ns = shift_hi - shift_lo + 1;
+    const size_t n = (size_t)cg.nw * ns;
+    if (n == 0) return RB_OK;
+    int rc = ensure(c, c->d_seedinfo, n * sizeof(uint32_t));
+    if (rc) return rc;
+    launch_anchor_planes((const PlaneWord*)c->d_planes.p + cg.word_base, cg.L, cg.nw, shift_lo, ns, (uint32_t*)c->d_seedinfo.p, c->stream);
+    RB_CUDA(c, cudaMemcpyAsync(out, c->d_seedinfo.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RB_CUDA(c, cudaGetLastError());
+    return RB_OK;
+}
+
 int rb_measure_int_peak(rb_ctx* c, double* ops_per_s) {
     if (!c || !ops_per_s) return RB_E_ARG;
     RB_CUDA(c, cudaSetDevice(c->device));

@@ -523,6 +523,38 @@ void launch_merge_write(const DevBatch& b, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Anchor planes on request (generateAnchoredShiftXORs, parse_anchored_shiftxor.cpp:20-56): the host-side merges and
+// the per-seed stage of the reference read the anchored planes B_m (fasta_utils.cpp:143-161). One thread per
+// (word, shift), stateless: the run length in front of the word is found by looking back.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) anchor_plane_kernel(const PlaneWord* __restrict__ cw, int L, int nw, int s_lo, int ns,
+                                                           uint32_t* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)nw * ns) return;
+    const int w = (int)(t % nw), s = s_lo + (int)(t / nw);
+    const int K2 = 2 * s;
+    int lenL = 0;
+    for (int k = w - 1; k >= 0; --k) {
+        const uint32_t xa = x_word(cw, k, s) | anchor_endmask(k, L, s);
+        const int tr = clz32(~xa);
+        lenL += tr;
+        if (tr < 32 || lenL >= K2 + 32) break;
+    }
+    const uint32_t xa = x_word(cw, w, s) | anchor_endmask(w, L, s);
+    const uint32_t xan = x_word(cw, w + 1, s) | anchor_endmask(w + 1, L, s);
+    uint32_t a = anchor_word(cw, w, L, s, xa, xan, lenL);
+    const long long rem = (long long)L - 32ll * w;  // bits past the contig end are not part of the plane
+    if (rem < 32) a &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+    out[t] = a;
+}
+
+void launch_anchor_planes(const PlaneWord* cw, int L, int nw, int s_lo, int ns, uint32_t* out, cudaStream_t st) {
+    const long long n = (long long)nw * ns;
+    if (n == 0) return;
+    anchor_plane_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cw, L, nw, s_lo, ns, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Integer-pipe microbenchmark (roofline denominator of the scan): independent chains of funnel shifts and LOP3s,
 // the instruction mix of the bit-sliced scan. 16 ops per thread per inner step.
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,264 @@
+// ribbit-b200 host side: a drop-in replacement of ribbit's processSequence (fasta_utils.h:12, fasta_utils.cpp:59-250)
+// that takes the seed scan from the B200 library (include/ribbit_scan.h) instead of the four bit-at-a-time loops
+//   processShiftXORsPerfect              parse_perfect_shiftxor.cpp:146
+//   processShiftXORswithSubstitutions    parse_substitute_shiftxor.cpp:391
+//   generateAnchoredShiftXORs            parse_anchored_shiftxor.cpp:20
+//   processShiftXORsAnchored             parse_anchored_shiftxor.cpp:538
+// Everything that consumes the candidates stays the reference's own host C++ and is linked from its unmodified
+// objects: the order-dependent merges addSeedToSeedPositions{Perfect,Substitutions,Anchored} (+ mergeAllLists), the
+// per-seed motif calling (processSeed, processSeedMotifWise), SSW and the CIGAR code. Build: compile this file in
+// place of fasta_utils.cpp and link libribbit_scan.so (ribbit_b200/host/Makefile).
+//
+// No scan happens on the CPU here: without a usable CUDA device the program stops with an error.
+#include <boost/dynamic_bitset.hpp>
+
+#include <cstdint>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "fasta_utils.h"
+#include "global_variables.h"
+#include "parse_seed.h"
+#include "parse_smallmotif_seed.h"
+#include "ribbit_scan.h"
+#include "ssw_cpp.h"
+
+using namespace std;
+typedef vector<tuple<int, int, int, int>> SeedList;
+typedef boost::dynamic_bitset<> Bitset;
+
+// file-level functions of the reference that have external linkage but no header
+void addSeedToSeedPositionsPerfect(int seed_start, int seed_end, int motif_length, SeedList &seed_positions,
+                                   vector<Bitset> &motif_bsets, int bset_size);  // parse_perfect_shiftxor.cpp:47
+int addSeedToSeedPositionsSubstitutions(int seed_start, int seed_end, int motif_length, SeedList &seed_positions_perfect,
+                                        SeedList &seed_positions_substut, int *seedlen_cutoff, vector<Bitset> &motif_bsets,
+                                        int bset_size, int from_index, int seed_type);  // parse_substitute_shiftxor.cpp:18
+tuple<int, int> addSeedToSeedPositionsAnchored(int seed_start, int seed_end, int motif_length, SeedList &seed_positions_perfect,
+                                               SeedList &seed_positions_substut, SeedList &seed_positions_anchored,
+                                               int *seedlen_cutoffs, vector<Bitset> &motif_bsets, int bset_size,
+                                               tuple<int, int> from_indices, int seed_type);  // parse_anchored_shiftxor.cpp:113
+
+// the functions of fasta_utils.cpp that other reference files may reference
+void parseFai(string, int &, unordered_map<string, int> &) {}
+
+namespace {
+
+struct Gpu {
+    rb_ctx *ctx = nullptr;
+    int m_lo = 0, m_hi = 0;
+    ~Gpu() { if (ctx) rb_destroy(ctx); }
+};
+Gpu g_gpu;
+
+[[noreturn]] void die(const char *what, const rb_ctx *ctx) {
+    cerr << "ERROR: " << what << ": " << rb_last_error(ctx) << "\n";
+    exit(1);
+}
+
+rb_ctx *gpu_context() {
+    if (g_gpu.ctx && (g_gpu.m_lo != MINIMUM_MLEN || g_gpu.m_hi != MAXIMUM_MLEN)) { rb_destroy(g_gpu.ctx); g_gpu.ctx = nullptr; }
+    if (!g_gpu.ctx) {
+        rb_params p = {MINIMUM_MLEN, MAXIMUM_MLEN, 0, 0};
+        const char *dev = getenv("RIBBIT_CUDA_DEVICE");
+        g_gpu.ctx = rb_create(dev ? atoi(dev) : 0, &p);
+        if (!g_gpu.ctx) die("cannot create the GPU scan context", nullptr);
+        g_gpu.m_lo = MINIMUM_MLEN; g_gpu.m_hi = MAXIMUM_MLEN;
+    }
+    return g_gpu.ctx;
+}
+
+// A plane given as 32-base words (bit i of word w = position 32w+i) -> the reference's bitset, whose bit index is
+// L-1-position (fasta_utils.cpp:93). Block k of the bitset holds positions L-64(k+1) .. L-64k-1 in reversed order.
+inline uint64_t bits_at(const uint32_t *w, long nw, long p) {  // 64 positions starting at p (p may be negative)
+    uint64_t v = 0;
+    const long w0 = p >> 5;  // floor
+    const int sh = (int)(p & 31);
+    uint64_t a = (w0 >= 0 && w0 < nw) ? w[w0] : 0, b = (w0 + 1 >= 0 && w0 + 1 < nw) ? w[w0 + 1] : 0,
+             c = (w0 + 2 >= 0 && w0 + 2 < nw) ? w[w0 + 2] : 0;
+    v = (a >> sh) | (b << (32 - sh));
+    if (sh) v |= c << (64 - sh);
+    return v;
+}
+inline uint64_t rev64(uint64_t x) {
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    return __builtin_bswap64(x);
+}
+Bitset to_bitset(const uint32_t *w, long L) {
+    const long nw = (L + 31) / 32, nb = (L + 63) / 64;
+    vector<unsigned long> blocks((size_t)nb);
+    for (long k = 0; k < nb; ++k) blocks[(size_t)k] = rev64(bits_at(w, nw, L - 64 * (k + 1)));
+    Bitset b(blocks.begin(), blocks.end());
+    b.resize((size_t)L);
+    return b;
+}
+
+}  // namespace
+
+void processSequence(string &sequence_id, string &sequence, int window_length, int window_bitcount_threshold, int anchor_size,
+                     int continuous_ones_threshold, ostream &out) {
+    (void)window_length; (void)window_bitcount_threshold; (void)anchor_size;  // fixed in the reference: 8, 7 then 6, 3
+    START_TIME = time(0);
+    int sequence_length = (int)sequence.length();
+    rb_ctx *ctx = gpu_context();
+
+    // ---- the scan, on the GPU: K1 pack, K2 scan, K6 ordered streams -------------------------------------------
+    const int64_t off0 = 0;
+    const int32_t len0 = sequence_length;
+    if (rb_load_contigs(ctx, sequence.data(), &off0, &len0, 1) != RB_OK) die("rb_load_contigs", ctx);
+    rb_streams st;
+    if (rb_scan(ctx, &st) != RB_OK) die("rb_scan", ctx);
+    cerr << "Generated shift XORs!\t Time elapsed:" << difftime(time(0), START_TIME) << "secs\n";
+
+    // ---- planes for the host-side consumers (merge tie-breakers read popcounts of the match planes) -----------
+    const long nw = ((long)sequence_length + 31) / 32;
+    vector<uint32_t> hi((size_t)nw + 1), lo((size_t)nw + 1), nn((size_t)nw + 1);
+    if (rb_get_planes(ctx, 0, hi.data(), lo.data(), nn.data()) != RB_OK) die("rb_get_planes", ctx);
+    Bitset left_bset = to_bitset(hi.data(), sequence_length), right_bset = to_bitset(lo.data(), sequence_length),
+           N_bset = to_bitset(nn.data(), sequence_length);
+    // one-hot planes + per-base pointers: only the per-seed stage reads them (fasta_utils.cpp:83-115)
+    Bitset A(sequence_length, 0ull), T(sequence_length, 0ull), G(sequence_length, 0ull), C(sequence_length, 0ull);
+    vector<Bitset *> MATRIX;
+    MATRIX.reserve((size_t)sequence_length);
+    for (int i = 0; i < sequence_length; i++) {
+        const int bidx = (sequence_length - 1) - i;
+        switch (sequence[i]) {
+            case 'A': case 'a': MATRIX.push_back(&A); A[bidx] = 1; break;
+            case 'C': case 'c': MATRIX.push_back(&C); C[bidx] = 1; break;
+            case 'G': case 'g': MATRIX.push_back(&G); G[bidx] = 1; break;
+            case 'T': case 't': MATRIX.push_back(&T); T[bidx] = 1; break;
+            default: MATRIX.push_back(NULL); break;
+        }
+    }
+    vector<Bitset> lshift_xor_bsets;  // fasta_utils.cpp:117-122, word-parallel already in the reference
+    for (int i = MINIMUM_SHIFT; i <= MAXIMUM_SHIFT; i++)
+        lshift_xor_bsets.push_back(~(left_bset ^ (left_bset << (i))) & ~(right_bset ^ (right_bset << (i))));
+
+    SeedList seed_positions_perfect, seed_positions_substut, seed_positions_anchored;
+    const int bset_size = sequence_length;
+
+    // ---- perfect candidates -> the reference's merge (parse_perfect_shiftxor.cpp:182,202,219) ------------------
+    for (int64_t k = 0; k < st.n[RB_STREAM_PERFECT]; ++k) {
+        const rb_rec &r = st.rec[RB_STREAM_PERFECT][k];
+        addSeedToSeedPositionsPerfect(r.start, r.end, r.mlen, seed_positions_perfect, lshift_xor_bsets, bset_size);
+    }
+    cerr << "Total number of perfect seeds: " << seed_positions_perfect.size() << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+
+    // ---- substitution candidates (parse_substitute_shiftxor.cpp:445…568) ---------------------------------------
+    {
+        vector<int> cut((size_t)NMOTIFS);
+        for (int midx = 0; midx < NMOTIFS; midx++) cut[(size_t)midx] = ((midx + MINIMUM_MLEN) > 30) ? (midx + MINIMUM_MLEN) / 3 : 10;  // :423
+        int from_index = 0;
+        for (int64_t k = 0; k < st.n[RB_STREAM_SUBST]; ++k) {
+            const rb_rec &r = st.rec[RB_STREAM_SUBST][k];
+            if (r.flags & RB_REC_PSEUDO) {
+                // calls the scan elided: only their cursor effect (…:34-42) matters, and only the largest end counts
+                if (r.end >= 0) from_index = addSeedToSeedPositionsSubstitutions(r.end, r.end, MINIMUM_MLEN, seed_positions_perfect, seed_positions_substut, cut.data(), lshift_xor_bsets, bset_size, from_index, RANK_S);
+                continue;
+            }
+            from_index = addSeedToSeedPositionsSubstitutions(r.start, r.end, r.mlen, seed_positions_perfect, seed_positions_substut, cut.data(), lshift_xor_bsets, bset_size, from_index, RANK_S);
+        }
+    }
+    {
+        int failed = 0;
+        for (auto &s : seed_positions_perfect) failed += get<3>(s) == -1;
+        for (auto &s : seed_positions_substut) failed += get<3>(s) == -1;
+        cerr << "Total number of seeds considering substitutions: " << seed_positions_perfect.size() + seed_positions_substut.size() - failed << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+    }
+
+    // ---- anchored planes: anchors from the GPU, the 5-way OR as fasta_utils.cpp:146-160 -------------------------
+    {
+        vector<uint32_t> anchors((size_t)nw * NSHIFTS + 1);
+        if (rb_get_anchor_planes(ctx, 0, MINIMUM_SHIFT, MAXIMUM_SHIFT, anchors.data()) != RB_OK) die("rb_get_anchor_planes", ctx);
+        vector<Bitset> lsxor_anchor_bsets;
+        for (int s = 0; s < NSHIFTS; s++) lsxor_anchor_bsets.push_back(to_bitset(anchors.data() + (size_t)s * nw, sequence_length));
+        Bitset anchor_bset(sequence_length, 0ull);
+        for (int motif_length = MINIMUM_MLEN; motif_length <= MAXIMUM_MLEN; motif_length++) {
+            anchor_bset.reset();
+            int i = (motif_length > 2) ? motif_length - 2 : 1;
+            for (; i <= motif_length + 2; i++) {
+                const int shift_idx = i - MINIMUM_SHIFT;
+                if (i == motif_length) anchor_bset |= lshift_xor_bsets[shift_idx];
+                else anchor_bset |= lsxor_anchor_bsets[shift_idx];
+            }
+            lshift_xor_bsets[motif_length - MINIMUM_SHIFT] = anchor_bset;
+        }
+    }
+    cerr << "Generated anchored shift XORs!\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+
+    // ---- anchored candidates (parse_anchored_shiftxor.cpp:595…717) -----------------------------------------------
+    {
+        vector<int> cut((size_t)NMOTIFS);
+        for (int midx = 0; midx < NMOTIFS; midx++) {  // :572-573
+            cut[(size_t)midx] = ((midx + MINIMUM_MLEN) > 6) ? (midx + MINIMUM_MLEN) : 10;
+            if (midx + MINIMUM_MLEN >= 10) cut[(size_t)midx] = 0.9 * (midx + MINIMUM_MLEN);
+        }
+        tuple<int, int> from_indices = {0, 0};
+        for (int64_t k = 0; k < st.n[RB_STREAM_ANCHORED]; ++k) {
+            const rb_rec &r = st.rec[RB_STREAM_ANCHORED][k];
+            if (r.flags & RB_REC_PSEUDO) {
+                if (r.end >= 0) from_indices = addSeedToSeedPositionsAnchored(r.end, r.end, MINIMUM_MLEN, seed_positions_perfect, seed_positions_substut, seed_positions_anchored, cut.data(), lshift_xor_bsets, bset_size, from_indices, RANK_A);
+                continue;
+            }
+            const tuple<int, int> ret = addSeedToSeedPositionsAnchored(r.start, r.end, r.mlen, seed_positions_perfect, seed_positions_substut, seed_positions_anchored, cut.data(), lshift_xor_bsets, bset_size, from_indices, RANK_A);
+            if (!(r.flags & RB_REC_NOCOMMIT)) from_indices = ret;  // tail-flush calls whose result the reference drops (:688-719)
+        }
+    }
+    {
+        int failed = 0;
+        for (auto &s : seed_positions_perfect) failed += get<3>(s) == -1;
+        for (auto &s : seed_positions_substut) failed += get<3>(s) == -1;
+        for (auto &s : seed_positions_anchored) failed += get<3>(s) == -1;
+        cerr << "Total number of seeds considering indels: " << seed_positions_perfect.size() + seed_positions_substut.size() + seed_positions_anchored.size() - failed << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+    }
+    if (const char *cp2 = getenv("RB_CP2_OUT")) {  // checkpoint CP2 for the parity tests: the three lists, same format as oracle/cp_hooks.h
+        if (FILE *f = fopen(cp2, "ab")) {
+            int32_t h[5] = {0, -1, sequence_length, 0, 0};
+            fwrite(h, sizeof h, 1, f);
+            int tag = 11;
+            for (SeedList *l : {&seed_positions_perfect, &seed_positions_substut, &seed_positions_anchored}) {
+                for (auto &s : *l) { int32_t r[5] = {tag, get<0>(s), get<1>(s), get<2>(s), get<3>(s)}; fwrite(r, sizeof r, 1, f); }
+                ++tag;
+            }
+            fclose(f);
+        }
+        if (getenv("RB_CP_STOP_AFTER_CP2")) return;
+    }
+
+    // ---- per-seed stage: the reference's loop, fasta_utils.cpp:174-246 ------------------------------------------
+    StripedSmithWaterman::Aligner aligner;
+    StripedSmithWaterman::Filter filter;
+    StripedSmithWaterman::Alignment alignment;
+    tuple<int, int, int, int> seed;
+    int seed_start, seed_end, seed_mlen, seed_type;
+    uint64_t smallest; int smallest_type = -1;
+    size_t spidx_p = 0, spidx_s = 0, spidx_a = 0;
+    int processed_seeds = 0;
+    while (spidx_p < seed_positions_perfect.size() || spidx_s < seed_positions_substut.size() || spidx_a < seed_positions_anchored.size()) {
+        smallest = -1;
+        // the head with the smallest start wins; ties go to perfect, then substitution (fasta_utils.cpp:191-200)
+        if (spidx_p < seed_positions_perfect.size() && (smallest > get<0>(seed_positions_perfect[spidx_p]))) { smallest = get<0>(seed_positions_perfect[spidx_p]); smallest_type = RANK_P; }
+        if (spidx_s < seed_positions_substut.size() && (smallest > get<0>(seed_positions_substut[spidx_s]))) { smallest = get<0>(seed_positions_substut[spidx_s]); smallest_type = RANK_S; }
+        if (spidx_a < seed_positions_anchored.size() && (smallest > get<0>(seed_positions_anchored[spidx_a]))) { smallest = get<0>(seed_positions_anchored[spidx_a]); smallest_type = RANK_A; }
+        if (smallest_type == RANK_P) { seed = seed_positions_perfect[spidx_p]; ++spidx_p; }
+        else if (smallest_type == RANK_S) { seed = seed_positions_substut[spidx_s]; ++spidx_s; }
+        else if (smallest_type == RANK_A) { seed = seed_positions_anchored[spidx_a]; ++spidx_a; }
+        seed_type = get<3>(seed);
+        if (seed_type == -1) continue;
+        seed_start = get<0>(seed); seed_end = get<1>(seed); seed_mlen = get<2>(seed);
+        if (seed_end - seed_start >= 0.9 * seed_mlen) {  // :224
+            processed_seeds += 1;
+            if (seed_mlen <= 10)
+                processSeedMotifWise(tuple<int, int>{seed_start, seed_end}, seed_mlen, seed_type, sequence_id, sequence, sequence_length,
+                                     lshift_xor_bsets[seed_mlen - MINIMUM_SHIFT], left_bset, right_bset, N_bset, continuous_ones_threshold, out, aligner, filter, alignment);
+            else
+                processSeed(tuple<int, int>{seed_start, seed_end}, seed_mlen, seed_type, sequence_id, sequence, sequence_length,
+                            lshift_xor_bsets[seed_mlen - MINIMUM_SHIFT], left_bset, right_bset, N_bset, continuous_ones_threshold, out, MATRIX, aligner, filter, alignment);
+        }
+    }
+    cerr << "Total number of seeds that are processed for alignment: " << processed_seeds << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+}

@@ -20,7 +20,7 @@ STREAM_NAMES = ("perfect", "subst", "anchored")
 
 EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
            "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes",
-           "rb_measure_int_peak")
+           "rb_measure_int_peak", "rb_get_anchor_planes")
 
 
 class RbParams(ctypes.Structure):
@@ -87,6 +87,8 @@ def load_library(path=LIB_PATH):
     lib.rb_filter_seeds.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.rb_measure_int_peak.restype = ctypes.c_int
     lib.rb_measure_int_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    lib.rb_get_anchor_planes.restype = ctypes.c_int
+    lib.rb_get_anchor_planes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     lib.rb_get_planes.restype = ctypes.c_int
     lib.rb_get_planes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
@@ -202,6 +204,15 @@ class Scanner:
         hi = np.zeros(max(nw, 1), np.uint32); lo = np.zeros(max(nw, 1), np.uint32); nn = np.zeros(max(nw, 1), np.uint32)
         self._check(self.lib.rb_get_planes(self.ctx, contig, hi.ctypes.data, lo.ctypes.data, nn.ctypes.data))
         return hi[:nw], lo[:nw], nn[:nw]
+
+    def anchor_planes(self, contig, shift_lo, shift_hi):
+        """(shift_hi-shift_lo+1, nw) uint32: anchor planes A_s of one contig, computed on the device."""
+        nw = (int(self.lengths[contig]) + 31) // 32
+        out = np.zeros((shift_hi - shift_lo + 1, max(nw, 1)), dtype=np.uint32)
+        if nw:
+            out = np.zeros((shift_hi - shift_lo + 1, nw), dtype=np.uint32)
+            self._check(self.lib.rb_get_anchor_planes(self.ctx, contig, shift_lo, shift_hi, out.ctypes.data))
+        return out[:, :nw]
 
     def filter_seeds(self, seeds):
         """seeds: (n,4) int32 rows (contig, start, end, mlen) -> (n,2) int32 rows (end_trunc, longest_run)."""
