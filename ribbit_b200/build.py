@@ -54,10 +54,18 @@ def build_oracle():
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
 
 
+def build_host():
+    """baseline/_ref/ribbit_gpu: the reference's host code (unmodified, from /root/reference) + the GPU processSequence.
+    Needs the reference sources, so it is only (re)built in the build container; the binary travels with the snapshot."""
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-s", "-C", os.path.join(HERE, "host")], check=True)
+
+
 def build_all(verbose=False):
     build_cuda(verbose=verbose)
     build_emulator()
     build_oracle()
+    build_host()
 
 
 if __name__ == "__main__":

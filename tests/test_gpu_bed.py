@@ -51,3 +51,45 @@ def test_cli_flags_are_the_references(golden):
     assert rc == 0 and bed == g["bed"].tobytes()
     r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
     assert b"Please specify an input fasta file" in r.stderr
+
+
+def _large_cases():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "golden_large.json")))
+
+
+@pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="baseline/_ref/ribbit_gpu is built in the build container")
+@pytest.mark.parametrize("name", ["c1_1mbp_default", "c1_300k_l12", "c2_1mbp_nruns", "c4_500k_p070"])
+def test_mbp_scale_bed_digest_matches_the_reference(name):
+    """BASELINE.json config shapes at 0.3-1 Mbp: md5 of the BED and of the merged seed lists vs the unmodified reference
+    (tests/golden/make_golden_large.py); the kept candidates of the C-ABI streams vs the reference's call log."""
+    import hashlib
+    from ribbit_b200 import scan
+    c = _large_cases()[name]
+    seq = getattr(synth, c["gen"])(**c["kwargs"])
+    assert hashlib.md5(seq).hexdigest() == c["seq_md5"], "synthetic input not reproduced"
+    mlo, mhi = 2, 100
+    # CP1: kept records of the three streams
+    sc = scan.Scanner(mlo, mhi)
+    sc.load([seq])
+    res = sc.scan()
+    for s in range(3):
+        a, _ = res[s]
+        real = a[(a["flags"] & (scan.REC_DROPPED | scan.REC_PSEUDO)) == 0]
+        rows = np.stack([real["start"], real["end"], real["mlen"].astype(np.int32)], axis=1).astype("<i4")
+        md5, n = c["cp1_kept"][str(s + 1)]
+        assert len(rows) == n and hashlib.md5(rows.tobytes()).hexdigest() == md5, "stream %d" % s
+    sc.close()
+    # CP2 + CP3 through the drop-in program
+    with tempfile.TemporaryDirectory() as td:
+        fa = os.path.join(td, "x.fa"); bed = os.path.join(td, "o.bed"); cp2 = os.path.join(td, "cp2.bin")
+        synth.write_fasta(fa, [seq])
+        r = subprocess.run([EXE, "-i", fa, "-o", bed, *c["flags"]], env=dict(os.environ, RB_CP2_OUT=cp2),
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=1200)
+        assert r.returncode == 0, r.stderr[-500:]
+        raw = np.fromfile(cp2, dtype=np.int32).reshape(-1, 5)
+        lists = raw[raw[:, 0] >= 11].copy()
+        lists[:, 0] -= 10
+        assert len(lists) == c["cp2_rows"] and hashlib.md5(lists.astype("<i4").tobytes()).hexdigest() == c["cp2_md5"]
+        b = open(bed, "rb").read()
+        assert b.count(b"\n") == c["bed_rows"] and hashlib.md5(b).hexdigest() == c["bed_md5"]
