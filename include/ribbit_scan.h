@@ -130,14 +130,16 @@ int rb_get_timing(const rb_ctx *ctx, rb_timing *out);
  * this GPU sustains, measured with a register-only microbenchmark of the scan's instruction mix. */
 int rb_measure_int_peak(rb_ctx *ctx, double *ops_per_s);
 
-/* Seed filter of processSeed / processSeedMotifWise (parse_seed.cpp:344-367, parse_smallmotif_seed.cpp:216-235):
- * for each seed (contig, start, end, mlen) returns the N-truncated end and the longest run of 1s of the anchored
- * plane B_mlen (fasta_utils.cpp:143-161) over [start, end'). */
+/* K5 — the per-seed gate of processSeed / processSeedMotifWise (parse_seed.cpp:344-367,
+ * parse_smallmotif_seed.cpp:216-235), batched: for each seed (contig, start, end, mlen) with end + mlen <= L (seeds are
+ * clamped so by the merges, parse_perfect_shiftxor.cpp:137) returns the length of the seed sequence after truncation
+ * at the first N in [start, end + mlen) and the longest run of 1s of the anchored plane B_mlen
+ * (fasta_utils.cpp:143-161) over [start, end). The reference drops a seed when longest_run < 3 (ribbit.cpp:191). */
 typedef struct rb_seed {
     int32_t contig, start, end, mlen;
 } rb_seed;
 typedef struct rb_seedinfo {
-    int32_t end_trunc;    /* end after truncation at the first N in [start, end + mlen) */
+    int32_t seq_len;      /* seed_sequence_length (parse_seed.cpp:347-353) */
     int32_t longest_run;  /* longestContinuousMatches (parse_seed.cpp:26-44) */
 } rb_seedinfo;
 int rb_filter_seeds(rb_ctx *ctx, const rb_seed *seeds, int64_t n, rb_seedinfo *out);

@@ -476,8 +476,26 @@ int rb_measure_int_peak(rb_ctx* c, double* ops_per_s) {
 }
 
 int rb_filter_seeds(rb_ctx* c, const rb_seed* seeds, int64_t n, rb_seedinfo* out) {
-    (void)seeds; (void)n; (void)out;
-    return fail(c, RB_E_STATE, "rb_filter_seeds: not available in this build");
+    if (!c || n < 0 || (n > 0 && (!seeds || !out))) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_filter_seeds: planes exist after rb_scan_device");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    for (int64_t i = 0; i < n; ++i) {
+        const rb_seed& s = seeds[i];
+        if (s.contig < 0 || s.contig >= c->batch.n_contigs || s.mlen < c->lay.m_lo || s.mlen > c->lay.m_hi || s.start < 0 ||
+            s.end < s.start || (long long)s.end + s.mlen > c->contigs[s.contig].L)
+            return fail(c, RB_E_ARG, "rb_filter_seeds: seed %lld out of range", (long long)i);
+    }
+    if (n == 0) return RB_OK;
+    int rc = ensure(c, c->d_seeds, (size_t)n * sizeof(rb_seed));
+    if (rc) return rc;
+    rc = ensure(c, c->d_seedinfo, (size_t)n * sizeof(rb_seedinfo));
+    if (rc) return rc;
+    RB_CUDA(c, cudaMemcpyAsync(c->d_seeds.p, seeds, (size_t)n * sizeof(rb_seed), cudaMemcpyHostToDevice, c->stream));
+    launch_seed_filter(c->batch, c->d_seeds.p, n, c->d_seedinfo.p, c->stream);
+    RB_CUDA(c, cudaMemcpyAsync(out, c->d_seedinfo.p, (size_t)n * sizeof(rb_seedinfo), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RB_CUDA(c, cudaGetLastError());
+    return RB_OK;
 }
 
 }  // extern "C"

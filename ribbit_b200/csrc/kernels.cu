@@ -527,11 +527,20 @@ void launch_merge_write(const DevBatch& b, cudaStream_t st) {
 // the per-seed stage of the reference read the anchored planes B_m (fasta_utils.cpp:143-161). One thread per
 // (word, shift), stateless: the run length in front of the word is found by looking back.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t anchor_word_stateless(const PlaneWord* __restrict__ cw, int L, int w, int s);
 __global__ void __launch_bounds__(256) anchor_plane_kernel(const PlaneWord* __restrict__ cw, int L, int nw, int s_lo, int ns,
                                                            uint32_t* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)nw * ns) return;
     const int w = (int)(t % nw), s = s_lo + (int)(t / nw);
+    uint32_t a = anchor_word_stateless(cw, L, w, s);
+    const long long rem = (long long)L - 32ll * w;  // bits past the contig end are not part of the plane
+    if (rem < 32) a &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+    out[t] = a;
+}
+
+// stateless anchor word A_s[w] (shared by the plane export and the seed filter)
+__device__ __forceinline__ uint32_t anchor_word_stateless(const PlaneWord* __restrict__ cw, int L, int w, int s) {
     const int K2 = 2 * s;
     int lenL = 0;
     for (int k = w - 1; k >= 0; --k) {
@@ -542,10 +551,55 @@ __global__ void __launch_bounds__(256) anchor_plane_kernel(const PlaneWord* __re
     }
     const uint32_t xa = x_word(cw, w, s) | anchor_endmask(w, L, s);
     const uint32_t xan = x_word(cw, w + 1, s) | anchor_endmask(w + 1, L, s);
-    uint32_t a = anchor_word(cw, w, L, s, xa, xan, lenL);
-    const long long rem = (long long)L - 32ll * w;  // bits past the contig end are not part of the plane
-    if (rem < 32) a &= rem <= 0 ? 0u : ((1u << rem) - 1u);
-    out[t] = a;
+    return anchor_word(cw, w, L, s, xa, xan, lenL);
+}
+
+// K5: the per-seed gate of processSeed / processSeedMotifWise (parse_seed.cpp:344-367, parse_smallmotif_seed.cpp:216-235):
+// length of the seed sequence after truncation at the first N in [start, end + mlen), and the longest run of 1s of the
+// anchored plane B_mlen over [start, end) (longestContinuousMatches, parse_seed.cpp:26-44). One thread per seed.
+__global__ void __launch_bounds__(128) seed_filter_kernel(DevBatch b, const int4* __restrict__ seeds, long long n, int2* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int4 sd = seeds[t];  // contig, start, end, mlen
+    const Contig cg = b.contigs[sd.x];
+    const PlaneWord* __restrict__ cw = b.planes + cg.word_base;
+    const int L = cg.L, start = sd.y, end = sd.z, m = sd.w;
+    // first N in [start, end + m)
+    int seq_len = (end - start) + m;
+    {
+        const int lim = min(end + m, L);
+        for (int w = start >> 5; 32 * w < lim; ++w) {
+            uint32_t nn = cw[w].n;
+            if (w == (start >> 5)) nn &= ~lowmask(start & 31);
+            if (nn) {
+                const int p = 32 * w + ctz32(nn);
+                if (p < lim) seq_len = p - start;
+                break;
+            }
+        }
+    }
+    // longest run of B_m over [start, end)
+    int best = 0, run = 0;
+    const int lo = (m > 2) ? m - 2 : 1;
+    for (int w = start >> 5; 32 * w < end; ++w) {
+        uint32_t bm = x_word(cw, w, m);
+        for (int s = lo; s <= m + 2; ++s)
+            if (s != m && s >= b.lay.s_lo && s <= b.lay.s_hi) bm |= anchor_word_stateless(cw, L, w, s);
+        if (w == (start >> 5)) bm &= ~lowmask(start & 31);
+        const int rem = end - 32 * w;
+        if (rem < 32) bm &= lowmask(rem);
+        const int first = max(start - 32 * w, 0), last = min(rem, 32);
+        if (bm == (lowmask(last) & ~lowmask(first))) { run += last - first; best = max(best, run); if (last < 32) run = 0; continue; }
+        for (int i = first; i < last; ++i) {
+            if ((bm >> i) & 1u) { ++run; best = max(best, run); } else run = 0;
+        }
+    }
+    out[t] = make_int2(seq_len, best);
+}
+
+void launch_seed_filter(const DevBatch& b, const void* seeds, long long n, void* out, cudaStream_t st) {
+    if (n == 0) return;
+    seed_filter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b, (const int4*)seeds, n, (int2*)out);
 }
 
 void launch_anchor_planes(const PlaneWord* cw, int L, int nw, int s_lo, int ns, uint32_t* out, cudaStream_t st) {

@@ -52,6 +52,8 @@ void launch_pack(const DevBatch& b, cudaStream_t st);
 void launch_scan(const DevBatch& b, cudaStream_t st);
 void launch_merge_count(const DevBatch& b, cudaStream_t st);   // M1 + M2
 void launch_merge_write(const DevBatch& b, cudaStream_t st);   // M3
+// K5: seeds = int4 {contig, start, end, mlen}[n] (device), out = int2 {seq_len, longest_run}[n] (device)
+void launch_seed_filter(const DevBatch& b, const void* seeds, long long n, void* out, cudaStream_t st);
 // anchor planes A_s, s = s_lo .. s_lo+ns-1, of one contig: out[(s - s_lo) * nw + w]
 void launch_anchor_planes(const PlaneWord* cw, int L, int nw, int s_lo, int ns, uint32_t* out, cudaStream_t st);
 // LOP3 + SHF warp-lane operations per second the device sustains (integer-pipe roofline denominator)

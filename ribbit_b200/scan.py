@@ -44,7 +44,7 @@ class RbSeed(ctypes.Structure):
 
 
 class RbSeedInfo(ctypes.Structure):
-    _fields_ = [("end_trunc", ctypes.c_int32), ("longest_run", ctypes.c_int32)]
+    _fields_ = [("seq_len", ctypes.c_int32), ("longest_run", ctypes.c_int32)]
 
 
 class RibbitScanError(RuntimeError):
@@ -215,7 +215,7 @@ class Scanner:
         return out[:, :nw]
 
     def filter_seeds(self, seeds):
-        """seeds: (n,4) int32 rows (contig, start, end, mlen) -> (n,2) int32 rows (end_trunc, longest_run)."""
+        """seeds: (n,4) int32 rows (contig, start, end, mlen) -> (n,2) int32 rows (seq_len, longest_run)."""
         seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 4)
         out = np.zeros((len(seeds), 2), dtype=np.int32)
         self._check(self.lib.rb_filter_seeds(self.ctx, seeds.ctypes.data, len(seeds), out.ctypes.data))

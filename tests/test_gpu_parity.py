@@ -130,3 +130,64 @@ def test_mid_size_properties(built):
     for x in (sc, sc2, sc3):
         x.close()
     assert t["launches"] >= 4
+
+
+def test_seed_filter_matches_reference_definition(built):
+    """K5 (rb_filter_seeds) against the definition in parse_seed.cpp:344-367 evaluated with the oracle's anchored plane."""
+    rng = np.random.default_rng(12)
+    seq = synth.fuzz_contig(rng, 30000, 0.002, m_range=(2, 60))
+    L = len(seq)
+    a = np.frombuffer(seq, dtype=np.uint8)
+    isn = ~np.isin(a, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+    sc = scan.Scanner(2, 100)
+    sc.load([seq])
+    res = sc.scan()
+    # seeds: kept candidates of the three streams (clamped as the merges do: end <= L - m)
+    seeds = []
+    for s in range(3):
+        r = res[s][0]
+        r = r[(r["flags"] & (scan.REC_DROPPED | scan.REC_PSEUDO)) == 0][::7][:150]
+        for st, en, m in zip(r["start"].tolist(), r["end"].tolist(), r["mlen"].tolist()):
+            en = min(en, L - m)
+            if en > st:
+                seeds.append((0, st, en, m))
+    seeds = np.array(seeds, dtype=np.int32)
+    got = sc.filter_seeds(seeds)
+    for (c, st, en, m), (seq_len, longest) in zip(seeds.tolist(), got.tolist()):
+        nn = np.flatnonzero(isn[st:en + m])
+        exp_len = int(nn[0]) if len(nn) else (en - st) + m
+        bm = ou.anchored_plane(seq, 2, 100, m, st, en)
+        runs = np.diff(np.flatnonzero(np.concatenate(([0], bm, [0])) == 0)) - 1
+        assert seq_len == exp_len and longest == int(runs.max(initial=0)), (st, en, m)
+    sc.close()
+
+
+def test_anchor_planes_match_oracle(built):
+    rng = np.random.default_rng(13)
+    seq = synth.fuzz_contig(rng, 5000, 0.002, m_range=(2, 40)) + b"ACG" * 40
+    sc = scan.Scanner(2, 30)
+    sc.load([seq])
+    sc.scan()
+    planes = sc.anchor_planes(0, 1, 32)
+    L = len(seq)
+    pos = np.arange(L)
+    for m in (2, 3, 7, 16, 30):
+        bm = ou.anchored_plane(seq, 2, 30, m, 0, L)
+        hi, lo, _ = sc.planes(0)
+        code = (((hi[pos >> 5] >> (pos & 31).astype(np.uint32)) & 1) * 2 + ((lo[pos >> 5] >> (pos & 31).astype(np.uint32)) & 1)).astype(np.int64)
+        x = np.where(pos + m < L, code == np.concatenate([code[m:], np.zeros(m, np.int64)])[:L], code == 0)
+        got = x.copy()
+        for s in range(max(m - 2, 1) if m > 2 else 1, m + 3):
+            if s != m:
+                got |= ((planes[s - 1][pos >> 5] >> (pos & 31).astype(np.uint32)) & 1).astype(bool)
+        assert (got.astype(np.uint8) == bm).all(), m
+    sc.close()
+
+
+def test_sharded_scan_single_rank(built):
+    from ribbit_b200 import shard
+    rng = np.random.default_rng(4)
+    contigs = [synth.fuzz_contig(rng, int(L), 0.005) for L in (900, 0, 2500, 1200, 40)]
+    out = shard.scan_sharded(contigs, shard.gpu_scan_fn(2, 30), 0, 1)
+    for seq, got in zip(contigs, out):
+        _same(got, sm.expected_streams(seq, ou.scan_events(seq, 2, 30)))
