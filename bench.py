@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -218,12 +218,12 @@ def run_gpu(args):
 
     # ---- device-resident throughput: the input is in HBM, the three ordered streams stay in HBM ------------------
     sc.load_device(dev.data_ptr(), [L], keepalive=dev)
+    sampler = ClockSampler(local)
+    sampler.start()                       # clocks under load: sampled from the warm-up steps to the end of the timed region
     for _ in range(args.warmup):
         sc.scan_device()
     counts = sc.counts()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     per_step, scan_ms, pack_ms, merge_ms, launches, restarts = [], [], [], [], 0, 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
