@@ -301,7 +301,9 @@ struct LaneState {
     uint32_t x_prev, x_cur, x_nxt;  // X_s of words w-1, w, w+1
     int lenL;                       // anchor-view run length ending at the end of word w-1
     WinCarry cs, ca;
-    int pst;                        // perfect machine: start of the open run or -1 (last_starts)
+    int pst;                        // perfect machine: start of the open run or -1 (last_starts); slow words
+    int lastRS;                     // position of the latest run start of X_m; fast words
+    uint32_t pa2, pa6;              // previous word of "2 / 6 ones in a row ending here"
     WinState S, A;                  // valid while the previous word was a slow word
     EvCarry es, ea;                 // carries always valid; lastS valid while the previous word was a fast word
     uint32_t sm[7];                 // anchored keep filter: previous word of each smear level
@@ -397,28 +399,32 @@ RB_HD void win_to_fast(const WinState& st, int& lastS) {
     else if (st.cur != -1) lastS = st.cur + 7;
 }
 
+// "six ones in a row ending at t" of X_m, with carries; kept up to date in every word (fast and slow)
+RB_HD uint32_t six_ones(uint32_t x, uint32_t xs1, uint32_t& pa2, uint32_t& pa6) {
+    const uint32_t a2 = x & xs1;
+    const uint32_t a4 = a2 & fsl(pa2, a2, 2);
+    const uint32_t a6 = a4 & fsl(pa2, a2, 4);
+    const uint32_t a6s1 = fsl(pa6, a6, 1);  // six ones ending at t-1
+    pa2 = a2; pa6 = a6;
+    return a6s1;
+}
+// Perfect runs in a fast word (no N in reach, so G = X_m): a run that ends at t (X[t] = 0, X[t-1] = 1) and is at
+// least `cutP` long is a candidate (parse_perfect_shiftxor.cpp:190-208). Every cutoff is >= 6, so the run ends that
+// do not follow six ones are skipped without looking at the run start.
 template <class Sink>
-RB_HD void perfect_fast(Sink& sk, const IterCtx& it, const LaneCfg& cfg, uint32_t g, int& pst) {
+RB_HD void perfect_fast(Sink& sk, const IterCtx& it, const LaneCfg& cfg, uint32_t x, uint32_t x_prev, LaneState& st) {
     const int p0 = 32 * it.w;
-    const int lead = ctz32(~g), trail = clz32(~g);
-    const bool has = pst >= 0, whole = g == 0xFFFFFFFFu;
-    // the open run (if any) ends at bit `lead`; the other runs strictly inside the word can only reach cutoffs <= 30
-    uint32_t r = has ? (g & ~lowmask(lead)) : g;
-    r &= lowmask(32 - trail);
-    const uint32_t e2 = r & (r >> 1), e4 = e2 & (e2 >> 2);
-    const uint32_t pre = (cfg.cutP >= 8) ? (e4 & (e4 >> 4)) : (e4 & (e2 >> 4));  // runs >= 8 / >= 6
-    const bool ends = has && !whole && (p0 + lead - pst >= cfg.cutP);
-    if (ends || (pre != 0u && cfg.cutP <= 30)) {  // rare
-        if (ends) emit_perfect(sk, it, cfg, pst, p0 + lead, p0 + lead);
-        if (cfg.cutP <= 30)
-            while (r) {
-                const int a = ctz32(r);
-                const int len = ctz32(~(r >> a));
-                if (len >= cfg.cutP) emit_perfect(sk, it, cfg, p0 + a, p0 + a + len, p0 + a + len);
-                r &= ~(lowmask(len) << a);
-            }
+    const uint32_t xs1 = fsl(x_prev, x, 1);
+    const uint32_t sx = x & ~xs1, ex = ~x & xs1;
+    uint32_t cand = ex & six_ones(x, xs1, st.pa2, st.pa6);
+    while (cand) {  // rare
+        const int i = ctz32(cand);
+        cand &= cand - 1u;
+        const uint32_t sb = sx & lowmask(i);
+        const int a = sb ? p0 + 31 - clz32(sb) : st.lastRS;
+        if (p0 + i - a >= cfg.cutP) emit_perfect(sk, it, cfg, a, p0 + i, p0 + i);
     }
-    pst = whole ? (has ? pst : p0) : (trail > 0 ? p0 + 32 - trail : -1);
+    st.lastRS = sx ? p0 + 31 - clz32(sx) : st.lastRS;
 }
 
 // ---- slow word: the reference state machines bit by bit ----------------------------------------------------------
@@ -572,6 +578,7 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const I
         if (it.prev_slow) {
             win_to_fast(st.S, st.es.lastS);
             win_to_fast(st.A, st.ea.lastS);
+            if (st.pst >= 0) st.lastRS = st.pst;  // the run that is open at the word boundary
         }
         if (!it.emit_on) {
             // warm-up in fast words: pst is exact once a mismatch was seen; lastS once a component start was seen
@@ -580,7 +587,7 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const I
             if (sS != 0u || nine_fails(~passS, st.zS)) st.sync |= SYNC_S;
             if (sA != 0u || nine_fails(~passA, st.zA)) st.sync |= SYNC_A;
         }
-        perfect_fast(sk, it, cfg, x, st.pst);
+        perfect_fast(sk, it, cfg, x, st.x_prev, st);
         if (eS | sS) win_fast_events(sk, it, cfg, STREAM_S, sS, eS, 0u, st.es.lastS);
         // the smear looks back up to three words: trust it once four fast words in a row were seen
         if (eA | sA) win_fast_events(sk, it, cfg, STREAM_A, sA, eA, it.fastrun >= 4 ? killA : 0u, st.ea.lastS);
@@ -607,6 +614,7 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
         ev_step(passS, st.es, sS, eS, sSp);
         ev_step(passA, st.ea, sA, eA, sAp);
         (void)smear_step(cfg, st, sA, sAp);
+        (void)six_ones(x, fsl(st.x_prev, x, 1), st.pa2, st.pa6);
         if (machines_on) {
             {
                 const uint32_t prev_v31 = cw[it.w - 1].v >> 31;
@@ -660,6 +668,7 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
     st.cs.z = st.cs.o1 = st.cs.t1 = st.cs.o2 = st.cs.t2 = st.cs.u2 = 0u;
     st.ca = st.cs;
     st.pst = -1;
+    st.lastRS = -1; st.pa2 = st.pa6 = 0u;
     st.S.cur = st.S.ls = st.S.le = -1;
     st.A = st.S;
     // nothing before the contig start: "failing" windows; a cold start must not invent a run of failing windows
