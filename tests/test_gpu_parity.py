@@ -191,3 +191,15 @@ def test_sharded_scan_single_rank(built):
     out = shard.scan_sharded(contigs, shard.gpu_scan_fn(2, 30), 0, 1)
     for seq, got in zip(contigs, out):
         _same(got, sm.expected_streams(seq, ou.scan_events(seq, 2, 30)))
+
+
+def test_pipeline_two_contexts_gives_same_streams(built):
+    from ribbit_b200 import pipeline
+    rng = np.random.default_rng(21)
+    seqs = [synth.fuzz_contig(rng, 40000, 0.001) for _ in range(5)]
+    pipe = pipeline.ScanPipeline(2, 100, depth=2, copy=True)
+    bufs = [np.frombuffer(s + b"\0", dtype=np.uint8) for s in seqs]
+    futs = [pipe.submit_flat(b, [len(s)]) for b, s in zip(bufs, seqs)]
+    for s, f in zip(seqs, futs):
+        _same(scan.contig_streams(f.result(), 0), sm.expected_streams(s, ou.scan_events(s, 2, 100)))
+    pipe.close()
