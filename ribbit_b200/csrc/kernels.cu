@@ -503,6 +503,29 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
         src[k] = b.raw + m.off;
         n[k] = meta_total(m);
     }
+    int nrec = 0;
+    for (int k = 0; k < nbands; ++k) nrec += n[k];
+    constexpr int MAXL = 32;
+    if (nrec <= MAXL) {
+        // usual case: read every record once into a per-thread array, rank there
+        int4 loc[MAXL];
+        int t = 0;
+        for (int k = 0; k < nbands; ++k)
+            for (int i = 0; i < n[k]; ++i) loc[t++] = *reinterpret_cast<const int4*>(src[k] + i);
+        for (int i = 0; i < nrec; ++i) {
+            const int4 r = loc[i];
+            const int s = (r.z >> REC_STREAM_SHIFT) & 3;
+            int rank = 0;
+            for (int q = 0; q < nrec; ++q) rank += ((((loc[q].z >> REC_STREAM_SHIFT) & 3) == s) & (loc[q].w < r.w)) ? 1 : 0;
+            Rec rr;
+            rr.start = r.x; rr.end = r.y; rr.mflags = r.z; rr.key = r.w;
+            const Rec f = finalize_rec(rr, bi.w);
+            int4 o4;
+            o4.x = f.start; o4.y = f.end; o4.z = f.mflags; o4.w = f.key;
+            *reinterpret_cast<int4*>(b.dst + sbase[s] + o[s] + bi.pseudo[s] + rank) = o4;
+        }
+        return;
+    }
     for (int k = 0; k < nbands; ++k)
         for (int i = 0; i < n[k]; ++i) {
             const Rec r = src[k][i];
