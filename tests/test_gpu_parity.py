@@ -203,3 +203,63 @@ def test_pipeline_two_contexts_gives_same_streams(built):
     for s, f in zip(seqs, futs):
         _same(scan.contig_streams(f.result(), 0), sm.expected_streams(s, ou.scan_events(s, 2, 100)))
     pipe.close()
+
+
+def test_c5_shape_many_short_contigs(built):
+    """BASELINE.json configs[4] shape (1 kb contigs, -m 1 -M 6), scaled to 20 000 contigs in one batch: a sample of contigs
+    against the oracle (the reference itself segfaults on this shape after logging CP1), the rest through
+    batch-independence (the same contig scanned alone gives the same streams)."""
+    contigs = synth.contigs_c5(n=20000, length=1000, seed=5)
+    sc = scan.Scanner(1, 6)
+    sc.load(contigs)
+    res = sc.scan()
+    t = sc.timing()
+    rng = np.random.default_rng(0)
+    for i in rng.choice(len(contigs), 60, replace=False).tolist() + [0, 1, 2, 3, len(contigs) - 1]:
+        _same(scan.contig_streams(res, i), sm.expected_streams(contigs[i], ou.scan_events(contigs[i], 1, 6)), "contig %d" % i)
+    for s in range(3):
+        off = res[s][1]
+        assert off[0] == 0 and off[-1] == len(res[s][0]) and (np.diff(off) >= 0).all()
+    sc.close()
+    assert t["launches"] >= 4
+
+
+def test_c3_shape_multi_contig_batch_matches_single_scans(built):
+    """Several contigs of different sizes in one batch (configs[2] shape, scaled): identical to scanning each alone."""
+    contigs = [synth.contig_c2(L, seed=100 + i) for i, L in enumerate([600_000, 50_000, 1_200_000, 333_333])]
+    sc = scan.Scanner(2, 100)
+    sc.load(contigs)
+    res = sc.scan()
+    for i, seq in enumerate(contigs):
+        one = scan.Scanner(2, 100, chunk_words=211)
+        one.load([seq])
+        r1 = one.scan()
+        for s in range(3):
+            a = res[s][0][res[s][1][i]:res[s][1][i + 1]]
+            assert len(a) == len(r1[s][0]) and (a == r1[s][0]).all(), (i, s)
+        one.close()
+    sc.close()
+
+
+def test_full_size_c2_properties(built):
+    """The bench workload itself (46.7 Mbp): stream invariants, and agreement of a window in the middle of the contig with
+    the oracle run on that window plus context (candidates fully inside the window, away from its ends)."""
+    L = 46_700_000
+    seq = synth.contig_c2(L, seed=21)
+    sc = scan.Scanner(2, 100)
+    sc.load([seq])
+    res = sc.scan()
+    a0, a1 = 30_000_000, 30_060_000
+    ctx = 4000
+    sub = seq[a0 - ctx:a1 + ctx]
+    exp = sm.expected_streams(sub, ou.scan_events(sub, 2, 100))
+    for s in range(3):
+        a = res[s][0]
+        real = a[(a["flags"] & scan.REC_PSEUDO) == 0]
+        assert (np.diff(real["time"].astype(np.int64)) >= 0).all()
+        mine = real[(real["start"] >= a0) & (real["end"] < a1) & (real["flags"] == 0)]
+        rows = np.stack([mine["start"] - (a0 - ctx), mine["end"] - (a0 - ctx), mine["mlen"]], axis=1).astype(np.int64)
+        e = exp[s + 1]
+        e = e[(e[:, 3] == 0) & (e[:, 0] >= ctx) & (e[:, 1] < ctx + (a1 - a0))][:, :3]
+        assert len(rows) == len(e) and (rows == e).all(), s
+    sc.close()
