@@ -176,6 +176,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
     }
 
     const int guard = b.lay.guard;
+    // lanes at the edge of an item have no neighbour on that side
+    const uint32_t mk_m2 = j < 2 ? 0u : 0xFFFFFFFFu, mk_m1 = j < 1 ? 0u : 0xFFFFFFFFu;
+    const uint32_t mk_p1 = j + 1 >= BW ? 0u : 0xFFFFFFFFu, mk_p2 = j + 2 >= BW ? 0u : 0xFFFFFFFFu;
     for (;;) {
         // ---- end of the chunk: tail flush (last chunk of a contig), record count -------------------------------
         if (active && w >= ch.w1) {
@@ -243,10 +246,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
         // anchor words of the neighbouring shifts (same item): lanes j-2, j-1, j+1, j+2
         uint32_t a_m2 = __shfl_up_sync(0xFFFFFFFFu, a, 2), a_m1 = __shfl_up_sync(0xFFFFFFFFu, a, 1);
         uint32_t a_p1 = __shfl_down_sync(0xFFFFFFFFu, a, 1), a_p2 = __shfl_down_sync(0xFFFFFFFFu, a, 2);
-        if (j < 2) a_m2 = 0u;
-        if (j < 1) a_m1 = 0u;
-        if (j + 1 >= BW) a_p1 = 0u;
-        if (j + 2 >= BW) a_p2 = 0u;
+        a_m2 &= mk_m2; a_m1 &= mk_m1; a_p1 &= mk_p1; a_p2 &= mk_p2;
         if (badmask) {
             // the warm-up did not reach a history-free state: start earlier
             H = min(H * 4, we);
@@ -283,10 +283,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
                     const uint32_t af = lane_phase1_fast(cfg, st, cw, w, L);
                     uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
                     uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
-                    if (j < 2) f_m2 = 0u;
-                    if (j < 1) f_m1 = 0u;
-                    if (j + 1 >= BW) f_p1 = 0u;
-                    if (j + 2 >= BW) f_p2 = 0u;
+                    f_m2 &= mk_m2; f_m1 &= mk_m1; f_p1 &= mk_p1; f_p2 &= mk_p2;
                     fastrun = min(fastrun + 1, 4);
                     IterCtx it;
                     it.w = w; it.L = L; it.emit_on = 1; it.slow = 0; it.prev_slow = 0; it.fastrun = fastrun;

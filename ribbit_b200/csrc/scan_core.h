@@ -89,7 +89,14 @@ RB_HD uint32_t fslc(uint32_t lo, uint32_t hi, int k) {
     return k >= 32 ? lo : fsl(lo, hi, k);
 #endif
 }
-RB_HD uint32_t lowmask(int nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
+// the low `nbits` bits set, 0 <= nbits <= 32
+RB_HD uint32_t lowmask(int nbits) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - nbits);  // (0 : ~0) >> (32 - nbits), shift clamped to 32
+#else
+    return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
+#endif
+}
 
 struct LaneCfg {
     int s;       // shift handled by this lane (>= 1), 0 = idle lane
@@ -282,19 +289,18 @@ struct WinState {
 //                                    (parse_substitute_shiftxor.cpp:475-530)
 // The component emitted at E-bit t is (ls, le) = (ts - 7, t - 8) with ts the latest S bit before t.
 struct EvCarry {
-    uint32_t F, r2, r4, r8, P, S;  // previous word
-    int lastS;                     // position of the latest S bit so far
+    uint32_t r2, r4, r8, P, S;  // previous word
+    int lastS;                  // position of the latest S bit so far
 };
 RB_HD void ev_step(uint32_t P, EvCarry& c, uint32_t& S, uint32_t& E, uint32_t& Sprev) {
-    const uint32_t F = ~P;
-    const uint32_t r2 = F & fsl(c.F, F, 1);
+    const uint32_t r2 = ~(P | fsl(c.P, P, 1));  // two failing windows in a row
     const uint32_t r4 = r2 & fsl(c.r2, r2, 2);
     const uint32_t r8 = r4 & fsl(c.r4, r4, 4);
     const uint32_t R81 = fsl(c.r8, r8, 1);
     S = P & R81;
     E = fsl(c.P, P, 9) & R81;
     Sprev = c.S;
-    c.F = F; c.r2 = r2; c.r4 = r4; c.r8 = r8; c.P = P; c.S = S;
+    c.r2 = r2; c.r4 = r4; c.r8 = r8; c.P = P; c.S = S;
 }
 
 struct LaneState {
@@ -672,8 +678,9 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
     st.S.cur = st.S.ls = st.S.le = -1;
     st.A = st.S;
     // nothing before the contig start: "failing" windows; a cold start must not invent a run of failing windows
-    st.es.F = st.es.r2 = st.es.r4 = st.es.r8 = (q == 0) ? 0xFFFFFFFFu : 0u;
-    st.es.P = st.es.S = 0u;
+    st.es.r2 = st.es.r4 = st.es.r8 = (q == 0) ? 0xFFFFFFFFu : 0u;
+    st.es.P = (q == 0) ? 0u : 0xFFFFFFFFu;
+    st.es.S = 0u;
     st.es.lastS = -1;
     st.ea = st.es;
     for (int i = 0; i < 7; ++i) st.sm[i] = 0u;
