@@ -1,5 +1,5 @@
-// ribbit-b200: per-lane scan logic shared by the sm_100a kernels (scan_kernels.cu) and by the CPU warp
-// emulator that tests/ uses to check the kernel logic without a GPU (tests/emu/emu_scan.cpp).
+// ribbit-b200: per-lane scan logic shared by the sm_100a kernels (kernels.cu) and by the CPU warp emulator that
+// tests/ uses to check the kernel logic without a GPU (tests/emu/emu_scan.cpp).
 //
 // Mapping: one warp lane owns one shift s of one band; a lane whose shift is a motif size m
 // of the band additionally runs the three seed machines of the reference for that m:
@@ -8,9 +8,15 @@
 //   anchored  parse_anchored_shiftxor.cpp:538-726     (8-window, >=6 matches, Y = B_m)
 // with  X_s  fasta_utils.cpp:117-122,  anchors A_s  parse_anchored_shiftxor.cpp:20-56,
 //       B_m  fasta_utils.cpp:143-161.
-// A lane walks the words (32 positions each) of its chunk in order. Words whose eight-position windows are all
-// valid ("fast" words: no N within [32w-7, 32w+31], inside the contig) are handled bit-parallel; every other word
-// ("slow" word) is handled bit-serially with the reference's state machine verbatim.
+// A lane walks the words (32 positions each) of its chunk in order, all backward-looking state in registers.
+//   FAST words (word_is_fast: every window ending in this and the previous word is evaluated, not the last word of
+//   the contig) are handled bit-parallel: window pass masks (fail_ge2 / fail_ge3), component start / end masks
+//   (ev_step), exact length filter (smear_step), run ends after six ones (perfect_fast); only candidates that reach
+//   the consumer's cutoff are touched individually.
+//   SLOW words (near N, contig start and end) go bit by bit through the reference's state machines verbatim
+//   (lane_phase2, win_slow_bit, win_tail), which reproduces every quirk of SURVEY.md A.6.
+// A fast -> slow transition rebuilds the machines' state by a warm-up that ends at the slow word; slow -> fast
+// converts the machine state (win_to_fast).
 #ifndef RB_SCAN_CORE_H
 #define RB_SCAN_CORE_H
 
