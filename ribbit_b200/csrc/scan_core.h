@@ -384,25 +384,23 @@ RB_HD uint32_t smear_step(const LaneCfg& cfg, LaneState& st, uint32_t S, uint32_
 // ---- fast word -----------------------------------------------------------------------------------------------------
 // Emits the components whose E bit lies in this word and that reach the consumer's length cutoff; the others only
 // contribute their emission time (Sink::dropped). S/E are this word's masks, Sprev the previous word's S mask.
+// Survivors of the keep filter (bits of x) of one stream, checked exactly and emitted: the component that ends at
+// E-bit i is (ls, le) = (ts - 7, p0 + i - 8), ts = the latest S bit before i. Returns the bits that were emitted.
 template <class Sink>
-RB_HD void win_fast_events(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, uint32_t S, uint32_t E,
-                           uint32_t kill, int& lastS) {
-    const int cut = (stream == STREAM_S) ? cfg.cutS : cfg.cutA;
-    const int p0 = 32 * it.w;
-    uint32_t x = it.emit_on ? (E & ~kill) : 0u, kept = 0u;
-    while (x) {  // exact check of the survivors
+RB_HD uint32_t kept_events(Sink& sk, int stream, int s, int cut, int p0, uint32_t S, uint32_t x, int lastS) {
+    uint32_t kept = 0u;
+    while (x) {
         const int i = ctz32(x);
         x &= x - 1u;
         const uint32_t sb = S & lowmask(i);
         const int ts = sb ? p0 + 31 - clz32(sb) : lastS;
         const int ls = ts - 7, le = p0 + i - 8;
         if (le - ls >= cut) {
-            sk.rec(stream, ls, le, cfg.s, 0, (i << 18) | (cfg.s << 2));
+            sk.rec(stream, ls, le, s, 0, (i << 18) | (s << 2));
             kept |= 1u << i;
         }
     }
-    sk.dropped_mask(stream, E & ~kept);
-    lastS = S ? p0 + 31 - clz32(S) : lastS;
+    return kept;
 }
 
 // lastS of the bit-parallel view from the reference machine's state (slow word -> fast word)
@@ -420,25 +418,6 @@ RB_HD uint32_t six_ones(uint32_t x, uint32_t xs1, uint32_t& pa2, uint32_t& pa6) 
     pa2 = a2; pa6 = a6;
     return a6s1;
 }
-// Perfect runs in a fast word (no N in reach, so G = X_m): a run that ends at t (X[t] = 0, X[t-1] = 1) and is at
-// least `cutP` long is a candidate (parse_perfect_shiftxor.cpp:190-208). Every cutoff is >= 6, so the run ends that
-// do not follow six ones are skipped without looking at the run start.
-template <class Sink>
-RB_HD void perfect_fast(Sink& sk, const IterCtx& it, const LaneCfg& cfg, uint32_t x, uint32_t x_prev, LaneState& st) {
-    const int p0 = 32 * it.w;
-    const uint32_t xs1 = fsl(x_prev, x, 1);
-    const uint32_t sx = x & ~xs1, ex = ~x & xs1;
-    uint32_t cand = ex & six_ones(x, xs1, st.pa2, st.pa6);
-    while (cand) {  // rare
-        const int i = ctz32(cand);
-        cand &= cand - 1u;
-        const uint32_t sb = sx & lowmask(i);
-        const int a = sb ? p0 + 31 - clz32(sb) : st.lastRS;
-        if (p0 + i - a >= cfg.cutP) emit_perfect(sk, it, cfg, a, p0 + i, p0 + i);
-    }
-    st.lastRS = sx ? p0 + 31 - clz32(sx) : st.lastRS;
-}
-
 // ---- slow word: the reference state machines bit by bit ----------------------------------------------------------
 template <class Sink>
 RB_HD void win_slow_bit(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, int p, int nbit, int vbit, int pass,
@@ -599,10 +578,32 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const I
             if (sS != 0u || nine_fails(~passS, st.zS)) st.sync |= SYNC_S;
             if (sA != 0u || nine_fails(~passA, st.zA)) st.sync |= SYNC_A;
         }
-        perfect_fast(sk, it, cfg, x, st.x_prev, st);
-        if (eS | sS) win_fast_events(sk, it, cfg, STREAM_S, sS, eS, 0u, st.es.lastS);
+        // candidates of this word: everything that needs per-bit work is gathered into one rarely taken region
+        const int p0 = 32 * it.w;
+        const uint32_t xs1 = fsl(st.x_prev, x, 1);
+        const uint32_t sx = x & ~xs1;                                           // perfect runs start here
+        const uint32_t cand = ~x & xs1 & six_ones(x, xs1, st.pa2, st.pa6);     // run ends that follow six ones
         // the smear looks back up to three words: trust it once four fast words in a row were seen
-        if (eA | sA) win_fast_events(sk, it, cfg, STREAM_A, sA, eA, it.fastrun >= 4 ? killA : 0u, st.ea.lastS);
+        const uint32_t xS = it.emit_on ? eS : 0u;
+        const uint32_t xA = it.emit_on ? (eA & ~(it.fastrun >= 4 ? killA : 0u)) : 0u;
+        uint32_t keptS = 0u, keptA = 0u;
+        if (cand | xS | xA) {
+            uint32_t c = cand;
+            while (c) {  // perfect runs (parse_perfect_shiftxor.cpp:190-208): every cutoff is >= 6
+                const int i = ctz32(c);
+                c &= c - 1u;
+                const uint32_t sb = sx & lowmask(i);
+                const int a = sb ? p0 + 31 - clz32(sb) : st.lastRS;
+                if (p0 + i - a >= cfg.cutP) emit_perfect(sk, it, cfg, a, p0 + i, p0 + i);
+            }
+            keptS = kept_events(sk, STREAM_S, cfg.s, cfg.cutS, p0, sS, xS, st.es.lastS);
+            keptA = kept_events(sk, STREAM_A, cfg.s, cfg.cutA, p0, sA, xA, st.ea.lastS);
+        }
+        sk.dropped_mask(STREAM_S, eS & ~keptS);
+        sk.dropped_mask(STREAM_A, eA & ~keptA);
+        st.lastRS = sx ? p0 + 31 - clz32(sx) : st.lastRS;
+        st.es.lastS = sS ? p0 + 31 - clz32(sS) : st.es.lastS;
+        st.ea.lastS = sA ? p0 + 31 - clz32(sA) : st.ea.lastS;
     }
     st.x_prev = st.x_cur;
     st.x_cur = st.x_nxt;
