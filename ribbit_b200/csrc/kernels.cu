@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
                     const uint32_t vcur = cw[w].v;
                     if ((vprev & vcur) != 0xFFFFFFFFu || w == cg.nw - 1 || prev_slow) break;
                     vprev = vcur;
-                    const uint32_t af = lane_phase1_fast(cfg, st, cw, w, L);
+                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L);
                     uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
                     uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
                     f_m2 &= mk_m2; f_m1 &= mk_m1; f_p1 &= mk_p1; f_p2 &= mk_p2;

@@ -178,6 +178,17 @@ RB_HD uint32_t x_word_cached(const PlaneWord* cw, int w, int s, XCache& xc) {
     return ~(th | tl);
 }
 
+// same, when the previous call was for word w-1 (tight loop): the cache is known to be valid
+RB_HD uint32_t x_word_next(const PlaneWord* cw, int w, int s, XCache& xc) {
+    const int off = s >> 5, sh = s & 31;
+    const PlaneWord o = cw[w];
+    const PlaneWord b = cw[w + off + 1];
+    const uint32_t th = o.h ^ fsr(xc.h, b.h, sh);
+    const uint32_t tl = o.l ^ fsr(xc.l, b.l, sh);
+    xc.h = b.h; xc.l = b.l; xc.idx = w + off + 1;
+    return ~(th | tl);
+}
+
 // positions p >= L - s never close an anchor run (parse_anchored_shiftxor.cpp:37): force them to 1 so that the
 // run that reaches L-1-s looks unbounded and is dropped by the "< 2*s" test.
 RB_HD uint32_t anchor_endmask(int w, int L, int s) {
@@ -507,9 +518,10 @@ RB_HD uint32_t lane_phase1(const LaneCfg& cfg, LaneState& st, const PlaneWord* c
 // Phase 1 for emitting words (warm-up bookkeeping not needed). Common case in straight-line code: no run touching
 // this word can reach 2s positions and the word is not near the contig end; then A_s[w] = the positions of X_s that
 // lie in a run of at least 3 (anchor_size, parse_anchored_shiftxor.cpp:44). Everything else takes anchor_word.
-RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
+template <bool SEQ>
+RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
     if (cfg.s == 0) return 0u;
-    st.x_nxt = x_word_cached(cw, w + 1, cfg.s, st.xc);
+    st.x_nxt = SEQ ? x_word_next(cw, w + 1, cfg.s, st.xc) : x_word_cached(cw, w + 1, cfg.s, st.xc);
     const uint32_t x = st.x_cur, xn = st.x_nxt, xp = st.x_prev;
     const int K2 = 2 * cfg.s;
     if ((w + 1 >= cfg.wm) | (x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu)) {  // rare: whole words of ones, contig end
@@ -552,6 +564,14 @@ RB_HD int nine_fails(uint32_t nz, int& zrun) {
     return hit;
 }
 
+RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
+    return lane_phase1_fast_t<false>(cfg, st, cw, w, L);
+}
+// the previous call (either phase-1 variant) was for word w-1
+RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
+    return lane_phase1_fast_t<true>(cfg, st, cw, w, L);
+}
+
 // Phase 2 of a fast word (it.slow == 0, machines on) (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so
 // o.v is all ones and the N plane is not consulted.
 template <class Sink>
@@ -584,7 +604,9 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const I
         const uint32_t sx = x & ~xs1;                                           // perfect runs start here
         const uint32_t cand = ~x & xs1 & six_ones(x, xs1, st.pa2, st.pa6);     // run ends that follow six ones
         // the smear looks back up to three words: trust it once four fast words in a row were seen
-        const uint32_t xS = it.emit_on ? eS : 0u;
+        // substitution cutoff is >= 10 (parse_substitute_shiftxor.cpp:423): a component whose S bit is 9 or 10 back
+        // has length 8 or 9 and is below it
+        const uint32_t xS = it.emit_on ? (eS & ~(fsl(sSp, sS, 9) | fsl(sSp, sS, 10))) : 0u;
         const uint32_t xA = it.emit_on ? (eA & ~(it.fastrun >= 4 ? killA : 0u)) : 0u;
         uint32_t keptS = 0u, keptA = 0u;
         if (cand | xS | xA) {
