@@ -495,32 +495,43 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     const int nbands = b.lay.nbands;
     const Rec* src[8];
     int n[8];
-    for (int k = 0; k < nbands; ++k) {
-        const Meta m = b.meta[(long long)k * b.n_buckets + gb];
-        src[k] = b.raw + m.off;
-        n[k] = meta_total(m);
-    }
     int nrec = 0;
-    for (int k = 0; k < nbands; ++k) nrec += n[k];
-    constexpr int MAXL = 32;
-    if (nrec <= MAXL) {
-        // usual case: read every record once into a per-thread array, rank there
-        int4 loc[MAXL];
-        int t = 0;
-        for (int k = 0; k < nbands; ++k)
-            for (int i = 0; i < n[k]; ++i) loc[t++] = *reinterpret_cast<const int4*>(src[k] + i);
-        for (int i = 0; i < nrec; ++i) {
-            const int4 r = loc[i];
-            const int s = (r.z >> REC_STREAM_SHIFT) & 3;
-            int rank = 0;
-            for (int q = 0; q < nrec; ++q) rank += ((((loc[q].z >> REC_STREAM_SHIFT) & 3) == s) & (loc[q].w < r.w)) ? 1 : 0;
-            Rec rr;
-            rr.start = r.x; rr.end = r.y; rr.mflags = r.z; rr.key = r.w;
-            const Rec f = finalize_rec(rr, bi.w);
-            int4 o4;
-            o4.x = f.start; o4.y = f.end; o4.z = f.mflags; o4.w = f.key;
-            *reinterpret_cast<int4*>(b.dst + sbase[s] + o[s] + bi.pseudo[s] + rank) = o4;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // fully unrolled: src / n stay in registers
+        src[k] = b.raw;
+        n[k] = 0;
+        if (k < nbands) {
+            const Meta m = b.meta[(long long)k * b.n_buckets + gb];
+            src[k] = b.raw + m.off;
+            n[k] = meta_total(m);
         }
+        nrec += n[k];
+    }
+    // rank inside a stream = (number of records of the bucket with a smaller (stream, key)) - (records of lower streams)
+    const int lower[3] = {0, (int)(bi.n[0] - bi.pseudo[0]), (int)(bi.n[0] - bi.pseudo[0] + bi.n[1] - bi.pseudo[1])};
+    constexpr int MAXL = 48;
+    if (nrec <= MAXL) {
+        uint32_t keys[MAXL];  // (stream << 30) | key of every record of the bucket
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            for (int i = 0; i < n[k]; ++i) {
+                const int2 zw = *reinterpret_cast<const int2*>(reinterpret_cast<const int*>(src[k] + i) + 2);
+                keys[t++] = ((uint32_t)((zw.x >> REC_STREAM_SHIFT) & 3) << 30) | (uint32_t)zw.y;
+            }
+        t = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            for (int i = 0; i < n[k]; ++i) {
+                const int4 r = *reinterpret_cast<const int4*>(src[k] + i);
+                const uint32_t key = keys[t++];
+                const int s = (int)(key >> 30);
+                int rank = 0;
+                for (int q = 0; q < nrec; ++q) rank += keys[q] < key ? 1 : 0;
+                int4 o4;
+                o4.x = r.x; o4.y = r.y; o4.z = r.z & ((1 << REC_STREAM_SHIFT) - 1); o4.w = 32 * bi.w + (r.w >> 18);
+                *reinterpret_cast<int4*>(b.dst + sbase[s] + o[s] + bi.pseudo[s] + (rank - lower[s])) = o4;
+            }
         return;
     }
     for (int k = 0; k < nbands; ++k)
