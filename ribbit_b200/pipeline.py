@@ -3,7 +3,7 @@ H2D copy, the kernels and the D2H copy of consecutive batches (contigs) overlap.
 and pinned result buffers; ctypes releases the GIL during the library calls. Results of a batch stay valid until the
 same context is used again (every `depth`-th submission), so consume or copy them before that.
 
-    pipe = ScanPipeline(2, 100, device=0, depth=2)
+    pipe = ScanPipeline(2, 100, device=0, depth=3)
     futures = [pipe.submit_flat(buf, [L]) for buf in batches]     # buf: pinned uint8 numpy array
     for f in futures: streams = f.result()
 """
@@ -13,7 +13,7 @@ from . import scan
 
 
 class ScanPipeline:
-    def __init__(self, min_mlen=2, max_mlen=100, device=0, depth=2, copy=False):
+    def __init__(self, min_mlen=2, max_mlen=100, device=0, depth=3, copy=False):
         self.depth = depth
         self.copy = copy
         self.scanners = [scan.Scanner(min_mlen, max_mlen, device=device) for _ in range(depth)]
