@@ -461,86 +461,109 @@ __global__ void __launch_bounds__(1024) merge_scan_kernel(DevBatch b) {
     }
 }
 
+// Phase 1 (thread = bucket): stream offsets of every bucket of the block, pseudo records, per-contig offsets.
+// Phase 2 (thread = record): the block's raw records are spread evenly over the threads; each finds its bucket in the
+// shared prefix table, ranks itself among the bucket's records by (stream, time, mlen, seq) and writes its final form.
 __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
-    const long long gb = (long long)blockIdx.x * MERGE_BLOCK + threadIdx.x;
+    __shared__ uint32_t s_off[8][MERGE_BLOCK];          // first raw record of (band, bucket)
+    __shared__ unsigned short s_n[8][MERGE_BLOCK];      // raw records of (band, bucket)
+    __shared__ uint32_t s_pre[MERGE_BLOCK + 1];         // exclusive prefix of the buckets' raw record counts
+    __shared__ uint32_t s_dst[3][MERGE_BLOCK];          // first final record of (stream, bucket), relative to the block,
+                                                        // pseudo record and records of lower streams already discounted
+    __shared__ int s_w[MERGE_BLOCK];
+    __shared__ uint32_t s_wsum[MERGE_BLOCK / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long gb = (long long)blockIdx.x * MERGE_BLOCK + tid;
     const bool live = gb < b.n_buckets;
+    const int nbands = b.lay.nbands;
     BucketInfo bi;
     bi.c = 0; bi.w = 0;
     for (int s = 0; s < 3; ++s) { bi.n[s] = 0u; bi.pseudo[s] = 0u; }
     bi.emax[0] = bi.emax[1] = 0ull;
-    if (live) bi = bucket_info(b, gb);
+    uint32_t nrec = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_off[k][tid] = 0u; s_n[k][tid] = 0; }
+    if (live) {
+        bi = bucket_info(b, gb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < nbands) {
+                const Meta m = b.meta[(long long)k * b.n_buckets + gb];
+                const int n = meta_total(m);
+                s_off[k][tid] = m.off;
+                s_n[k][tid] = (unsigned short)n;
+                nrec += (uint32_t)n;
+            }
+    }
     unsigned xs[3], tot[3];
     unsigned long long xe[2], tote[2];
     block_scan(bi.n, bi.emax, xs, xe, tot, tote);
-    if (!live) return;
     const BlockPartial bp = b.partial[blockIdx.x];
     const BlockPartial total = b.partial[b.n_merge_blocks];
-    long long o[3];  // offsets inside each stream
-    for (int s = 0; s < 3; ++s) o[s] = (long long)bp.sum[s] + xs[s];
     const long long sbase[3] = {0ll, (long long)total.sum[0], (long long)(total.sum[0] + total.sum[1])};
-    if (bi.w == 0)
-        for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + bi.c] = o[s];
-    if (gb == b.n_buckets - 1)
-        for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + b.n_contigs] = o[s] + bi.n[s];
-    if (bi.n[0] + bi.n[1] + bi.n[2] == 0u) return;
+    // block prefix of the raw record counts
+    {
+        uint32_t v = nrec;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += t; }
+        if (lane == 31) s_wsum[warp] = v;
+        __syncthreads();
+        uint32_t pre = 0u;
+        for (int k = 0; k < warp; ++k) pre += s_wsum[k];
+        s_pre[tid] = pre + v - nrec;
+        if (tid == MERGE_BLOCK - 1) s_pre[MERGE_BLOCK] = pre + v;
+    }
+    s_w[tid] = bi.w;
+    {
+        const uint32_t lowerS = bi.n[0] - bi.pseudo[0], lowerA = lowerS + bi.n[1] - bi.pseudo[1];
+        s_dst[0][tid] = xs[0] + bi.pseudo[0];
+        s_dst[1][tid] = xs[1] + bi.pseudo[1] - lowerS;   // rank among all records of the bucket minus the lower streams
+        s_dst[2][tid] = xs[2] + bi.pseudo[2] - lowerA;
+    }
+    if (live) {
+        long long o[3];
+        for (int s = 0; s < 3; ++s) o[s] = (long long)bp.sum[s] + xs[s];
+        if (bi.w == 0)
+            for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + bi.c] = o[s];
+        if (gb == b.n_buckets - 1)
+            for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + b.n_contigs] = o[s] + bi.n[s];
+        for (int s = 1; s < 3; ++s)
+            if (bi.pseudo[s]) {
+                const unsigned long long e = umax64(bp.emax[s - 1], xe[s - 1]);
+                long long ee = -1;
+                if (e != 0ull && (int)(e >> 32) == bi.c) ee = (long long)(e & 0xFFFFFFFFull) - 1;
+                b.dst[sbase[s] + o[s]] = pseudo_rec(bi.w, ee);
+            }
+    }
+    __syncthreads();
 
-    for (int s = 1; s < 3; ++s)
-        if (bi.pseudo[s]) {
-            const unsigned long long e = umax64(bp.emax[s - 1], xe[s - 1]);
-            long long ee = -1;
-            if (e != 0ull && (int)(e >> 32) == bi.c) ee = (long long)(e & 0xFFFFFFFFull) - 1;
-            const Rec r = pseudo_rec(bi.w, ee);
-            b.dst[sbase[s] + o[s]] = r;
+    const uint32_t T = s_pre[MERGE_BLOCK];
+    for (uint32_t r = tid; r < T; r += MERGE_BLOCK) {
+        int lo = 0, hi = MERGE_BLOCK - 1;  // largest bucket with s_pre[bucket] <= r
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_pre[mid] <= r) lo = mid; else hi = mid - 1;
         }
-    const int nbands = b.lay.nbands;
-    const Rec* src[8];
-    int n[8];
-    int nrec = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {  // fully unrolled: src / n stay in registers
-        src[k] = b.raw;
-        n[k] = 0;
-        if (k < nbands) {
-            const Meta m = b.meta[(long long)k * b.n_buckets + gb];
-            src[k] = b.raw + m.off;
-            n[k] = meta_total(m);
-        }
-        nrec += n[k];
-    }
-    // rank inside a stream = (number of records of the bucket with a smaller (stream, key)) - (records of lower streams)
-    const int lower[3] = {0, (int)(bi.n[0] - bi.pseudo[0]), (int)(bi.n[0] - bi.pseudo[0] + bi.n[1] - bi.pseudo[1])};
-    constexpr int MAXL = 48;
-    if (nrec <= MAXL) {
-        uint32_t keys[MAXL];  // (stream << 30) | key of every record of the bucket
-        int t = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            for (int i = 0; i < n[k]; ++i) {
-                const int2 zw = *reinterpret_cast<const int2*>(reinterpret_cast<const int*>(src[k] + i) + 2);
-                keys[t++] = ((uint32_t)((zw.x >> REC_STREAM_SHIFT) & 3) << 30) | (uint32_t)zw.y;
+        const int bk = lo;
+        uint32_t idx = r - s_pre[bk];
+        int band = 0;
+        while (idx >= s_n[band][bk]) { idx -= s_n[band][bk]; ++band; }
+        const int4 rec = *reinterpret_cast<const int4*>(b.raw + s_off[band][bk] + idx);
+        const int st = (rec.z >> REC_STREAM_SHIFT) & 3;
+        const uint32_t key = ((uint32_t)st << 30) | (uint32_t)rec.w;
+        int rank = 0;
+        for (int k = 0; k < nbands; ++k) {
+            const int n = s_n[k][bk];
+            const int2* q = reinterpret_cast<const int2*>(reinterpret_cast<const int*>(b.raw + s_off[k][bk]) + 2);
+            for (int i = 0; i < n; ++i) {
+                const int2 zw = q[2 * i];  // .z, .w of record i (records are 16 bytes)
+                rank += ((((uint32_t)((zw.x >> REC_STREAM_SHIFT) & 3) << 30) | (uint32_t)zw.y) < key) ? 1 : 0;
             }
-        t = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            for (int i = 0; i < n[k]; ++i) {
-                const int4 r = *reinterpret_cast<const int4*>(src[k] + i);
-                const uint32_t key = keys[t++];
-                const int s = (int)(key >> 30);
-                int rank = 0;
-                for (int q = 0; q < nrec; ++q) rank += keys[q] < key ? 1 : 0;
-                int4 o4;
-                o4.x = r.x; o4.y = r.y; o4.z = r.z & ((1 << REC_STREAM_SHIFT) - 1); o4.w = 32 * bi.w + (r.w >> 18);
-                *reinterpret_cast<int4*>(b.dst + sbase[s] + o[s] + bi.pseudo[s] + (rank - lower[s])) = o4;
-            }
-        return;
-    }
-    for (int k = 0; k < nbands; ++k)
-        for (int i = 0; i < n[k]; ++i) {
-            const Rec r = src[k][i];
-            const int s = (r.mflags >> REC_STREAM_SHIFT) & 3;
-            const int rank = rank_in_bucket(r, src, n, nbands);
-            b.dst[sbase[s] + o[s] + bi.pseudo[s] + rank] = finalize_rec(r, bi.w);
         }
+        int4 o4;
+        o4.x = rec.x; o4.y = rec.y; o4.z = rec.z & ((1 << REC_STREAM_SHIFT) - 1); o4.w = 32 * s_w[bk] + (rec.w >> 18);
+        const uint32_t rel = s_dst[st][bk] + (uint32_t)rank;  // 32-bit wrap-around: s_dst may hold "offset - lower"
+        *reinterpret_cast<int4*>(b.dst + sbase[st] + (long long)bp.sum[st] + rel) = o4;
+    }
 }
 
 void launch_merge_count(const DevBatch& b, cudaStream_t st) {
