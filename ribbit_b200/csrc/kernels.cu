@@ -404,60 +404,54 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_count_kernel(DevBatch b) {
     }
 }
 
-// one block; serial over chunks of 1024 partials, which is plenty (n_merge_blocks ~ n_buckets / 256)
+// one block: every thread owns a contiguous range of the block partials (local prefix), one block-wide scan of the
+// per-thread totals, then the exclusive prefixes are written back; entry n_merge_blocks receives the totals
 __global__ void __launch_bounds__(1024) merge_scan_kernel(DevBatch b) {
     __shared__ unsigned long long s_w[5][32];
-    __shared__ unsigned long long s_carry[5];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 5) s_carry[threadIdx.x] = 0ull;
+    const int per = (b.n_merge_blocks + 1023) / 1024;
+    const int i0 = threadIdx.x * per, i1 = min(b.n_merge_blocks, i0 + per);
+    unsigned long long v[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+    for (int i = i0; i < i1; ++i) {
+        const BlockPartial p = b.partial[i];
+        v[0] += p.sum[0]; v[1] += p.sum[1]; v[2] += p.sum[2];
+        v[3] = umax64(v[3], p.emax[0]); v[4] = umax64(v[4], p.emax[1]);
+    }
+    unsigned long long ex[5], all[5];
+    for (int k = 0; k < 5; ++k) {
+        unsigned long long x = v[k];
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x = (k < 3) ? x + t : umax64(x, t);
+        }
+        if (lane == 31) s_w[k][warp] = x;
+        const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+        ex[k] = (k < 3) ? x - v[k] : (lane ? up : 0ull);  // exclusive inside the warp
+    }
     __syncthreads();
-    for (int base = 0; base < b.n_merge_blocks; base += 1024) {
-        const int i = base + threadIdx.x;
-        unsigned long long v[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
-        if (i < b.n_merge_blocks) {
-            const BlockPartial p = b.partial[i];
-            v[0] = p.sum[0]; v[1] = p.sum[1]; v[2] = p.sum[2]; v[3] = p.emax[0]; v[4] = p.emax[1];
+    for (int k = 0; k < 5; ++k) {
+        unsigned long long pre = 0ull, tot = 0ull;
+        for (int u = 0; u < 32; ++u) {
+            const unsigned long long x = s_w[k][u];
+            if (k < 3) { if (u < warp) pre += x; tot += x; }
+            else { if (u < warp) pre = umax64(pre, x); tot = umax64(tot, x); }
         }
-        unsigned long long inc[5];
-        for (int k = 0; k < 5; ++k) {
-            unsigned long long x = v[k];
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, x, d);
-                if (lane >= d) x = (k < 3) ? x + t : umax64(x, t);
-            }
-            inc[k] = x;
-            if (lane == 31) s_w[k][warp] = x;
-        }
-        __syncthreads();
-        unsigned long long ex[5], all[5];
-        for (int k = 0; k < 5; ++k) {
-            unsigned long long pre = s_carry[k], tot = s_carry[k];
-            for (int u = 0; u < 32; ++u) {
-                const unsigned long long x = s_w[k][u];
-                if (k < 3) { if (u < warp) pre += x; tot += x; }
-                else { if (u < warp) pre = umax64(pre, x); tot = umax64(tot, x); }
-            }
-            if (k < 3) ex[k] = pre + inc[k] - v[k];
-            else {
-                const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, inc[k], 1);
-                ex[k] = umax64(pre, lane ? up : 0ull);
-            }
-            all[k] = tot;
-        }
-        if (i < b.n_merge_blocks) {
-            BlockPartial p;
-            p.sum[0] = ex[0]; p.sum[1] = ex[1]; p.sum[2] = ex[2]; p.emax[0] = ex[3]; p.emax[1] = ex[4];
-            b.partial[i] = p;
-        }
-        __syncthreads();
-        if (threadIdx.x < 5) s_carry[threadIdx.x] = all[threadIdx.x];
-        __syncthreads();
+        ex[k] = (k < 3) ? ex[k] + pre : umax64(ex[k], pre);
+        all[k] = tot;
+    }
+    for (int i = i0; i < i1; ++i) {  // exclusive prefix of every partial of this thread's range
+        const BlockPartial p = b.partial[i];
+        BlockPartial o;
+        o.sum[0] = ex[0]; o.sum[1] = ex[1]; o.sum[2] = ex[2]; o.emax[0] = ex[3]; o.emax[1] = ex[4];
+        b.partial[i] = o;
+        ex[0] += p.sum[0]; ex[1] += p.sum[1]; ex[2] += p.sum[2];
+        ex[3] = umax64(ex[3], p.emax[0]); ex[4] = umax64(ex[4], p.emax[1]);
     }
     if (threadIdx.x == 0) {
         BlockPartial p;
-        p.sum[0] = s_carry[0]; p.sum[1] = s_carry[1]; p.sum[2] = s_carry[2]; p.emax[0] = s_carry[3]; p.emax[1] = s_carry[4];
+        p.sum[0] = all[0]; p.sum[1] = all[1]; p.sum[2] = all[2]; p.emax[0] = all[3]; p.emax[1] = all[4];
         b.partial[b.n_merge_blocks] = p;
-        b.totals[0] = (long long)s_carry[0]; b.totals[1] = (long long)s_carry[1]; b.totals[2] = (long long)s_carry[2];
+        b.totals[0] = (long long)all[0]; b.totals[1] = (long long)all[1]; b.totals[2] = (long long)all[2];
     }
 }
 
