@@ -198,7 +198,19 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the scan has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator is created; this program's stdout
+        # carries exactly one JSON line, so the banner goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
