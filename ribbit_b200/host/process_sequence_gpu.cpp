@@ -176,16 +176,13 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
         if (rb_get_anchor_planes(ctx, 0, MINIMUM_SHIFT, MAXIMUM_SHIFT, anchors.data()) != RB_OK) die("rb_get_anchor_planes", ctx);
         vector<Bitset> lsxor_anchor_bsets;
         for (int s = 0; s < NSHIFTS; s++) lsxor_anchor_bsets.push_back(to_bitset(anchors.data() + (size_t)s * nw, sequence_length));
-        Bitset anchor_bset(sequence_length, 0ull);
-        for (int motif_length = MINIMUM_MLEN; motif_length <= MAXIMUM_MLEN; motif_length++) {
-            anchor_bset.reset();
-            int i = (motif_length > 2) ? motif_length - 2 : 1;
-            for (; i <= motif_length + 2; i++) {
-                const int shift_idx = i - MINIMUM_SHIFT;
-                if (i == motif_length) anchor_bset |= lshift_xor_bsets[shift_idx];
-                else anchor_bset |= lsxor_anchor_bsets[shift_idx];
-            }
-            lshift_xor_bsets[motif_length - MINIMUM_SHIFT] = anchor_bset;
+        // B_m = X_m | A_i for the shifts i within two of m (from 1 when m <= 2), written over plane m in ascending m:
+        // planes m-2 and m-1 were already overwritten, but only their anchor planes are read (fasta_utils.cpp:146-160)
+        for (int m = MINIMUM_MLEN; m <= MAXIMUM_MLEN; ++m) {
+            Bitset bm = lshift_xor_bsets[m - MINIMUM_SHIFT];
+            for (int i = (m > 2) ? m - 2 : 1; i <= m + 2; ++i)
+                if (i != m) bm |= lsxor_anchor_bsets[i - MINIMUM_SHIFT];
+            lshift_xor_bsets[m - MINIMUM_SHIFT] = bm;
         }
     }
     cerr << "Generated anchored shift XORs!\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
@@ -229,36 +226,33 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
         if (getenv("RB_CP_STOP_AFTER_CP2")) return;
     }
 
-    // ---- per-seed stage: the reference's loop, fasta_utils.cpp:174-246 ------------------------------------------
+    // ---- per-seed stage (what fasta_utils.cpp:174-246 does): the three lists are walked head to head, the head with
+    // the smallest start goes first (ties: perfect, then substitution, then anchored); entries re-tagged -1 by the
+    // merges are skipped; seeds shorter than 0.9 motif lengths are not processed -----------------------------------
     StripedSmithWaterman::Aligner aligner;
     StripedSmithWaterman::Filter filter;
     StripedSmithWaterman::Alignment alignment;
-    tuple<int, int, int, int> seed;
-    int seed_start, seed_end, seed_mlen, seed_type;
-    uint64_t smallest; int smallest_type = -1;
-    size_t spidx_p = 0, spidx_s = 0, spidx_a = 0;
+    const SeedList *lists[3] = {&seed_positions_perfect, &seed_positions_substut, &seed_positions_anchored};
+    size_t head[3] = {0, 0, 0};
     int processed_seeds = 0;
-    while (spidx_p < seed_positions_perfect.size() || spidx_s < seed_positions_substut.size() || spidx_a < seed_positions_anchored.size()) {
-        smallest = -1;
-        // the head with the smallest start wins; ties go to perfect, then substitution (fasta_utils.cpp:191-200)
-        if (spidx_p < seed_positions_perfect.size() && (smallest > get<0>(seed_positions_perfect[spidx_p]))) { smallest = get<0>(seed_positions_perfect[spidx_p]); smallest_type = RANK_P; }
-        if (spidx_s < seed_positions_substut.size() && (smallest > get<0>(seed_positions_substut[spidx_s]))) { smallest = get<0>(seed_positions_substut[spidx_s]); smallest_type = RANK_S; }
-        if (spidx_a < seed_positions_anchored.size() && (smallest > get<0>(seed_positions_anchored[spidx_a]))) { smallest = get<0>(seed_positions_anchored[spidx_a]); smallest_type = RANK_A; }
-        if (smallest_type == RANK_P) { seed = seed_positions_perfect[spidx_p]; ++spidx_p; }
-        else if (smallest_type == RANK_S) { seed = seed_positions_substut[spidx_s]; ++spidx_s; }
-        else if (smallest_type == RANK_A) { seed = seed_positions_anchored[spidx_a]; ++spidx_a; }
-        seed_type = get<3>(seed);
-        if (seed_type == -1) continue;
-        seed_start = get<0>(seed); seed_end = get<1>(seed); seed_mlen = get<2>(seed);
-        if (seed_end - seed_start >= 0.9 * seed_mlen) {  // :224
-            processed_seeds += 1;
-            if (seed_mlen <= 10)
-                processSeedMotifWise(tuple<int, int>{seed_start, seed_end}, seed_mlen, seed_type, sequence_id, sequence, sequence_length,
-                                     lshift_xor_bsets[seed_mlen - MINIMUM_SHIFT], left_bset, right_bset, N_bset, continuous_ones_threshold, out, aligner, filter, alignment);
-            else
-                processSeed(tuple<int, int>{seed_start, seed_end}, seed_mlen, seed_type, sequence_id, sequence, sequence_length,
-                            lshift_xor_bsets[seed_mlen - MINIMUM_SHIFT], left_bset, right_bset, N_bset, continuous_ones_threshold, out, MATRIX, aligner, filter, alignment);
-        }
+    for (;;) {
+        int pick = -1;
+        for (int k = 0; k < 3; ++k)
+            if (head[k] < lists[k]->size() && (pick < 0 || get<0>((*lists[k])[head[k]]) < get<0>((*lists[pick])[head[pick]]))) pick = k;
+        if (pick < 0) break;
+        const tuple<int, int, int, int> seed = (*lists[pick])[head[pick]++];
+        int rank = get<3>(seed), mlen = get<2>(seed);
+        if (rank == -1) continue;
+        const int from = get<0>(seed), to = get<1>(seed);
+        if (!(to - from >= 0.9 * mlen)) continue;
+        ++processed_seeds;
+        Bitset &plane = lshift_xor_bsets[mlen - MINIMUM_SHIFT];
+        if (mlen <= 10)
+            processSeedMotifWise(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset,
+                                 right_bset, N_bset, continuous_ones_threshold, out, aligner, filter, alignment);
+        else
+            processSeed(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset, right_bset,
+                        N_bset, continuous_ones_threshold, out, MATRIX, aligner, filter, alignment);
     }
     cerr << "Total number of seeds that are processed for alignment: " << processed_seeds << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
 }
