@@ -263,3 +263,39 @@ def test_full_size_c2_properties(built):
         e = e[(e[:, 3] == 0) & (e[:, 0] >= ctx) & (e[:, 1] < ctx + (a1 - a0))][:, :3]
         assert len(rows) == len(e) and (rows == e).all(), s
     sc.close()
+
+
+def test_abi_error_behaviour(built):
+    import ctypes
+    lib = scan.load_library()
+    p = scan.RbParams(2, 100, 0, 0)
+    ctx = lib.rb_create(0, ctypes.byref(p))
+    assert ctx
+    out = scan.RbStreams()
+    assert lib.rb_scan_device(ctx) == -4 and b"no contigs loaded" in lib.rb_last_error(ctx)      # RB_E_STATE
+    assert lib.rb_fetch(ctx, ctypes.byref(out)) == -4
+    lengths = np.array([-5], dtype=np.int32); offs = np.zeros(1, dtype=np.int64); buf = np.zeros(8, dtype=np.uint8)
+    assert lib.rb_load_contigs(ctx, buf.ctypes.data, offs.ctypes.data, lengths.ctypes.data, 1) == -5  # RB_E_RANGE
+    assert lib.rb_load_contigs(ctx, None, None, None, 3) == -1                                         # RB_E_ARG
+    assert lib.rb_load_contigs(ctx, None, None, None, 0) == 0                                          # empty batch is fine
+    assert lib.rb_scan(ctx, ctypes.byref(out)) == 0 and out.n_contigs == 0 and list(out.n) == [0, 0, 0]
+    lib.rb_destroy(ctx)
+    assert not lib.rb_create(99, ctypes.byref(p)) and b"not available" in lib.rb_last_error(None)
+
+
+def test_python_cli_writes_kept_candidates(built, tmp_path):
+    from ribbit_b200 import __main__ as cli
+    rng = np.random.default_rng(31)
+    seqs = [synth.fuzz_contig(rng, 3000, 0.002), synth.fuzz_contig(rng, 1200, 0.0)]
+    fa = tmp_path / "x.fa"
+    synth.write_fasta(str(fa), seqs, names=["one", "two"])
+    outp = tmp_path / "c.tsv"
+    assert cli.main(["scan", "-i", str(fa), "-o", str(outp), "-m", "2", "-M", "40"]) == 0
+    rows = [l.split("\t") for l in open(outp).read().splitlines()]
+    for name, seq in zip(["one", "two"], seqs):
+        exp = sm.expected_streams(seq, ou.scan_events(seq, 2, 40))
+        for s, tag in ((1, "P"), (2, "S"), (3, "A")):
+            mine = [(int(r[2]), int(r[3]), int(r[4])) for r in rows if r[0] == name and r[1] == tag]
+            e = exp[s]
+            e = e[(e[:, 3] & (scan.REC_DROPPED | scan.REC_PSEUDO)) == 0]
+            assert mine == [tuple(x) for x in e[:, :3].tolist()]
