@@ -176,9 +176,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
     }
 
     const int guard = b.lay.guard;
-    // lanes at the edge of an item have no neighbour on that side
-    const uint32_t mk_m2 = j < 2 ? 0u : 0xFFFFFFFFu, mk_m1 = j < 1 ? 0u : 0xFFFFFFFFu;
-    const uint32_t mk_p1 = j + 1 >= BW ? 0u : 0xFFFFFFFFu, mk_p2 = j + 2 >= BW ? 0u : 0xFFFFFFFFu;
+    // The neighbour anchors of lanes at the edge of an item need no masking: lanes 0 and 1 of an item are halo
+    // shifts (never motif lanes) and a motif lane has j + 2 <= mpb + 3 < BW (layout.h), so every value a motif lane
+    // reads comes from its own item.
     for (;;) {
         // ---- end of the chunk: tail flush (last chunk of a contig), record count -------------------------------
         if (active && w >= ch.w1) {
@@ -246,7 +246,6 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
         // anchor words of the neighbouring shifts (same item): lanes j-2, j-1, j+1, j+2
         uint32_t a_m2 = __shfl_up_sync(0xFFFFFFFFu, a, 2), a_m1 = __shfl_up_sync(0xFFFFFFFFu, a, 1);
         uint32_t a_p1 = __shfl_down_sync(0xFFFFFFFFu, a, 1), a_p2 = __shfl_down_sync(0xFFFFFFFFu, a, 2);
-        a_m2 &= mk_m2; a_m1 &= mk_m1; a_p1 &= mk_p1; a_p2 &= mk_p2;
         if (badmask) {
             // the warm-up did not reach a history-free state: start earlier
             H = min(H * 4, we);
@@ -274,19 +273,20 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
 
         // ---- tight path: consecutive fast, emitting words of a whole-warp item ---------------------------------
         if constexpr (BW == 32) {
-            if (active && !badmask && w > we && w >= e0 && !(b.debug & 1)) {  // word `we` (state check) goes through the general path
+            // word `we` (state check) and the first fast words of a stretch (keep filter not yet trusted) go through the
+            // general path; the tight loop stops before the contig's tail zone (anchor view differs from X_s there)
+            if (active && !badmask && w > we && w >= e0 && fastrun >= 4 && !prev_slow && !(b.debug & 1)) {
                 uint32_t vprev = cw[w - 1].v;
-                while (w < ch.w1) {
+                const int wend = min(min(ch.w1, cg.nw - 1), ((L - b.lay.s_hi) >> 5) - 1);
+                while (w < wend) {
                     const uint32_t vcur = cw[w].v;
-                    if ((vprev & vcur) != 0xFFFFFFFFu || w == cg.nw - 1 || prev_slow) break;
+                    if ((vprev & vcur) != 0xFFFFFFFFu) break;
                     vprev = vcur;
                     const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L);
                     uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
                     uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
-                    f_m2 &= mk_m2; f_m1 &= mk_m1; f_p1 &= mk_p1; f_p2 &= mk_p2;
-                    fastrun = min(fastrun + 1, 4);
                     IterCtx it;
-                    it.w = w; it.L = L; it.emit_on = 1; it.slow = 0; it.prev_slow = 0; it.fastrun = fastrun;
+                    it.w = w; it.L = L; it.emit_on = 1; it.slow = 0; it.prev_slow = 0; it.fastrun = 4;
                     sk.counts = 0u; sk.dS = 0; sk.dA = 0;
                     lane_phase2_fast(sk, cfg, st, it, f_m2, f_m1, f_p1, f_p2);
                     const uint32_t counts = __reduce_add_sync(0xFFFFFFFFu, sk.counts);

@@ -524,7 +524,8 @@ RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const Plane
     st.x_nxt = SEQ ? x_word_next(cw, w + 1, cfg.s, st.xc) : x_word_cached(cw, w + 1, cfg.s, st.xc);
     const uint32_t x = st.x_cur, xn = st.x_nxt, xp = st.x_prev;
     const int K2 = 2 * cfg.s;
-    if ((w + 1 >= cfg.wm) | (x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu)) {  // rare: whole words of ones, contig end
+    // SEQ: the caller keeps w + 1 below every lane's wm
+    if ((!SEQ && (w + 1 >= cfg.wm)) | (x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu)) {  // rare: whole words of ones, contig end
         const uint32_t xa = x | anchor_endmask(w, L, cfg.s);
         const uint32_t xan = xn | anchor_endmask(w + 1, L, cfg.s);
         if (xa != 0xFFFFFFFFu || st.lenL >= K2) st.sync |= SYNC_X;
