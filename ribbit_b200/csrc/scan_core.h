@@ -259,35 +259,46 @@ RB_HD uint32_t anchor_word(const PlaneWord* cw, int w, int L, int s, uint32_t xa
 }
 
 // carries of the bit-sliced "number of mismatches in the last 8 positions" counters (previous word)
+// The window tests need, of the previous word, only the top 1 / 2 / 4 bits of the bit-sliced partial counts; those
+// bits are functions of the previous word's zero mask alone (its top 7 bits), so the lane carries just that mask and
+// recomputes the partial counts (plain shifts: they issue on the FMA pipe), instead of carrying five or six words.
 struct WinCarry {
-    uint32_t z, o1, t1, o2, t2, u2;
+    uint32_t z;
 };
 
 // fail mask for ">= 7 of 8" (substitution pass): bit p set iff Y[p-7..p] holds >= 2 zeros
 RB_HD uint32_t fail_ge2(uint32_t y, WinCarry& c) {
-    const uint32_t z = ~y;
-    const uint32_t z1 = fsl(c.z, z, 1);
+    const uint32_t z = ~y, zp = c.z;
+    const uint32_t zp1 = zp << 1;
+    const uint32_t o1p = zp | zp1, t1p = zp & zp1;             // exact in the top bits, which is all that is read
+    const uint32_t o1p2 = o1p << 2;
+    const uint32_t o2p = o1p | o1p2, t2p = t1p | (t1p << 2) | (o1p & o1p2);
+    const uint32_t z1 = fsl(zp, z, 1);
     const uint32_t o1 = z | z1, t1 = z & z1;
-    const uint32_t o1s = fsl(c.o1, o1, 2), t1s = fsl(c.t1, t1, 2);
+    const uint32_t o1s = fsl(o1p, o1, 2), t1s = fsl(t1p, t1, 2);
     const uint32_t o2 = o1 | o1s;
     const uint32_t t2 = t1 | t1s | (o1 & o1s);
-    const uint32_t o2s = fsl(c.o2, o2, 4), t2s = fsl(c.t2, t2, 4);
+    const uint32_t o2s = fsl(o2p, o2, 4), t2s = fsl(t2p, t2, 4);
     const uint32_t t3 = t2 | t2s | (o2 & o2s);
-    c.z = z; c.o1 = o1; c.t1 = t1; c.o2 = o2; c.t2 = t2;
+    c.z = z;
     return t3;
 }
 // fail mask for ">= 6 of 8" (anchored pass): bit p set iff Y[p-7..p] holds >= 3 zeros
 RB_HD uint32_t fail_ge3(uint32_t y, WinCarry& c) {
-    const uint32_t z = ~y;
-    const uint32_t z1 = fsl(c.z, z, 1);
+    const uint32_t z = ~y, zp = c.z;
+    const uint32_t zp1 = zp << 1;
+    const uint32_t o1p = zp | zp1, t1p = zp & zp1;
+    const uint32_t o1p2 = o1p << 2, t1p2 = t1p << 2;
+    const uint32_t o2p = o1p | o1p2, t2p = t1p | t1p2 | (o1p & o1p2), u2p = (t1p & o1p2) | (o1p & t1p2);
+    const uint32_t z1 = fsl(zp, z, 1);
     const uint32_t o1 = z | z1, t1 = z & z1;
-    const uint32_t o1s = fsl(c.o1, o1, 2), t1s = fsl(c.t1, t1, 2);
+    const uint32_t o1s = fsl(o1p, o1, 2), t1s = fsl(t1p, t1, 2);
     const uint32_t o2 = o1 | o1s;
     const uint32_t t2 = t1 | t1s | (o1 & o1s);
     const uint32_t u2 = (t1 & o1s) | (o1 & t1s);
-    const uint32_t o2s = fsl(c.o2, o2, 4), t2s = fsl(c.t2, t2, 4), u2s = fsl(c.u2, u2, 4);
+    const uint32_t o2s = fsl(o2p, o2, 4), t2s = fsl(t2p, t2, 4), u2s = fsl(u2p, u2, 4);
     const uint32_t u3 = u2 | u2s | (t2 & o2s) | (o2 & t2s);
-    c.z = z; c.o1 = o1; c.t1 = t1; c.o2 = o2; c.t2 = t2; c.u2 = u2;
+    c.z = z;
     return u3;
 }
 
@@ -701,7 +712,7 @@ RB_HD void lane_tail(Sink& sk, const LaneCfg& cfg, LaneState& st, int L) {
 // start whose state becomes exact once the sync bits are set.
 RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int q) {
     st.x_prev = 0u; st.x_cur = 0u; st.x_nxt = 0u; st.lenL = 0;
-    st.cs.z = st.cs.o1 = st.cs.t1 = st.cs.o2 = st.cs.t2 = st.cs.u2 = 0u;
+    st.cs.z = 0u;
     st.ca = st.cs;
     st.pst = -1;
     st.lastRS = -1; st.pa2 = st.pa6 = 0u;
