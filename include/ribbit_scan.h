@@ -131,8 +131,8 @@ int rb_get_timing(const rb_ctx *ctx, rb_timing *out);
 int rb_measure_int_peak(rb_ctx *ctx, double *ops_per_s);
 
 /* K5 — the per-seed gate of processSeed / processSeedMotifWise (parse_seed.cpp:344-367,
- * parse_smallmotif_seed.cpp:216-235), batched: for each seed (contig, start, end, mlen) with end + mlen <= L (seeds are
- * clamped so by the merges, parse_perfect_shiftxor.cpp:137) returns the length of the seed sequence after truncation
+ * parse_smallmotif_seed.cpp:216-235), batched: for each seed (contig, start, end, mlen), end <= L (the merges clamp seeds to
+ * end + mlen <= L, parse_perfect_shiftxor.cpp:137) returns the length of the seed sequence after truncation
  * at the first N in [start, end + mlen) and the longest run of 1s of the anchored plane B_mlen
  * (fasta_utils.cpp:143-161) over [start, end). The reference drops a seed when longest_run < 3 (ribbit.cpp:191). */
 typedef struct rb_seed {

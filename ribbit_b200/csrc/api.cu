@@ -482,7 +482,7 @@ int rb_filter_seeds(rb_ctx* c, const rb_seed* seeds, int64_t n, rb_seedinfo* out
     for (int64_t i = 0; i < n; ++i) {
         const rb_seed& s = seeds[i];
         if (s.contig < 0 || s.contig >= c->batch.n_contigs || s.mlen < c->lay.m_lo || s.mlen > c->lay.m_hi || s.start < 0 ||
-            s.end < s.start || (long long)s.end + s.mlen > c->contigs[s.contig].L)
+            s.end < s.start || s.end > c->contigs[s.contig].L)
             return fail(c, RB_E_ARG, "rb_filter_seeds: seed %lld out of range", (long long)i);
     }
     if (n == 0) return RB_OK;

@@ -234,18 +234,32 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     StripedSmithWaterman::Alignment alignment;
     const SeedList *lists[3] = {&seed_positions_perfect, &seed_positions_substut, &seed_positions_anchored};
     size_t head[3] = {0, 0, 0};
-    int processed_seeds = 0;
+    vector<rb_seed> todo;     // in processing order
+    vector<int> todo_rank;
     for (;;) {
         int pick = -1;
         for (int k = 0; k < 3; ++k)
             if (head[k] < lists[k]->size() && (pick < 0 || get<0>((*lists[k])[head[k]]) < get<0>((*lists[pick])[head[pick]]))) pick = k;
         if (pick < 0) break;
         const tuple<int, int, int, int> seed = (*lists[pick])[head[pick]++];
-        int rank = get<3>(seed), mlen = get<2>(seed);
+        const int rank = get<3>(seed), mlen = get<2>(seed);
         if (rank == -1) continue;
         const int from = get<0>(seed), to = get<1>(seed);
         if (!(to - from >= 0.9 * mlen)) continue;
-        ++processed_seeds;
+        todo.push_back(rb_seed{0, from, to, mlen});
+        todo_rank.push_back(rank);
+    }
+    const int processed_seeds = (int)todo.size();
+    // K5: the gate both per-seed functions apply first (parse_seed.cpp:344-367, parse_smallmotif_seed.cpp:216-235) —
+    // longest run of 1s of the anchored plane over the seed below `continuous_ones_threshold` -> the reference returns
+    // before doing anything — evaluated for all seeds in one batch on the GPU; such seeds are not handed over at all.
+    vector<rb_seedinfo> info(todo.size());
+    const bool use_filter = !getenv("RIBBIT_NO_SEED_FILTER");
+    if (use_filter && !todo.empty() && rb_filter_seeds(ctx, todo.data(), (int64_t)todo.size(), info.data()) != RB_OK) die("rb_filter_seeds", ctx);
+    for (size_t k = 0; k < todo.size(); ++k) {
+        if (use_filter && info[k].longest_run < continuous_ones_threshold) continue;
+        int mlen = todo[k].mlen, rank = todo_rank[k];
+        const int from = todo[k].start, to = todo[k].end;
         Bitset &plane = lshift_xor_bsets[mlen - MINIMUM_SHIFT];
         if (mlen <= 10)
             processSeedMotifWise(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset,
