@@ -261,7 +261,7 @@ def run_gpu(args):
     # ribbit_b200.pipeline.ScanPipeline: three contexts on the GPU, so the copies of one step overlap the kernels of the
     # next, as when a genome is scanned contig by contig. All K results are complete inside the timed region.
     from ribbit_b200 import pipeline
-    pipe = pipeline.ScanPipeline(M_LO, M_HI, device=local, depth=3)
+    pipe = pipeline.ScanPipeline(M_LO, M_HI, device=local, depth=3, compact=True)
     for f in [pipe.submit_flat(host_np[:L + 1], [L]) for _ in range(4)]:
         f.result()
     barrier()
@@ -276,7 +276,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * L * args.steps / float(te.item()) / 1e9
-    d2h = int(sum(len(res[s][0]) for s in range(3)) * 16 + 3 * 2 * 8)
+    d2h = int(sum(len(res[s][0]) for s in range(3)) * 8 + 3 * 2 * 8)
     # the same without overlap: one context, load -> scan -> fetch back to back
     sc2 = scan.Scanner(M_LO, M_HI, device=local)
     sc2.load_flat(host_np[:L + 1], [L]); sc2.scan(copy=False)
@@ -317,7 +317,7 @@ def run_gpu(args):
                        "wall_ms_bracket": wall_ms, "warmup_restarts_per_step": restarts / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gbp/s", "h2d_bytes_per_step": int(L), "d2h_bytes_per_step": d2h,
-                    "what": "per step: rb_load_contigs (pinned host ASCII -> HBM) + rb_scan (kernels + D2H of the three streams); steps pipelined over 3 contexts (ribbit_b200.pipeline)",
+                    "what": "per step: rb_load_contigs (pinned host ASCII -> HBM) + rb_scan_device (kernels) + rb_fetch_compact (D2H of the three streams as 8-byte records); steps pipelined over 3 contexts (ribbit_b200.pipeline)",
                     "serial_one_context_gbps_per_gpu": e2e_serial},
             "gpu_launches": launches,
             "roofline": {"bound": "int", "kernel": "scan_kernel<32>", "achieved": achieved / 1e12, "peak": int_peak / 1e12,

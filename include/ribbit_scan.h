@@ -118,6 +118,31 @@ int rb_scan_device(rb_ctx *ctx);
 /* Copies the streams of the last rb_scan_device to pinned host memory. */
 int rb_fetch(rb_ctx *ctx, rb_streams *out);
 
+/* Compact form of the same streams for hosts that are bound by the PCIe / memory traffic of the result (8 instead of 16
+ * bytes per candidate): `time` is dropped (the order of the array is the call order), `end` = start + len.
+ *   len == 0xFFFF          the candidate is at least 65535 long: its `end` is in the `long_end` list of the stream
+ *                          (entries {index into rec8, end}, ascending index)
+ *   flags & RB_REC_PSEUDO  `start` holds the PSEUDO record's `end` value, len = 0 */
+typedef struct rb_rec8 {
+    int32_t start;
+    uint16_t len;
+    uint16_t mf;  /* mlen | flags << 12 */
+} rb_rec8;
+typedef struct rb_long_end {
+    int64_t index;
+    int64_t end;
+} rb_long_end;
+typedef struct rb_streams8 {
+    int32_t n_contigs;
+    int32_t reserved;
+    const rb_rec8 *rec[3];
+    const int64_t *contig_off[3];
+    int64_t n[3];
+    const rb_long_end *long_end[3];
+    int64_t n_long[3];
+} rb_streams8;
+int rb_fetch_compact(rb_ctx *ctx, rb_streams8 *out);
+
 /* rb_scan_device + rb_fetch. */
 int rb_scan(rb_ctx *ctx, rb_streams *out);
 

@@ -48,7 +48,7 @@ struct rb_ctx {
     const void* ascii_dev_ext = nullptr;
 
     DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
-        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo;
+        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long;
     DevBatch batch{};
 
     // pinned host results
@@ -56,6 +56,9 @@ struct rb_ctx {
     size_t h_rec_cap = 0;
     void* h_off = nullptr;
     size_t h_off_cap = 0;
+    void* h_long = nullptr;  // pinned: side list of long candidates + its counters
+    size_t h_long_cap = 0;
+    std::vector<rb_long_end> long_sorted[3];
     long long* h_small = nullptr;  // pinned: totals[3], counters[2]
     long long totals[3] = {0, 0, 0};
     rb_timing timing{};
@@ -280,10 +283,11 @@ void rb_destroy(rb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_chunks,
                       &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_raw, &c->d_counters,
-                      &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo};
+                      &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     if (c->h_off) cudaFreeHost(c->h_off);
+    if (c->h_long) cudaFreeHost(c->h_long);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -405,6 +409,58 @@ int rb_fetch(rb_ctx* c, rb_streams* out) {
         out->rec[s] = (const rb_rec*)c->h_rec + base;
         out->contig_off[s] = (const int64_t*)c->h_off + (size_t)s * (n + 1);
         out->n[s] = c->totals[s];
+        base += c->totals[s];
+    }
+    return RB_OK;
+}
+
+int rb_fetch_compact(rb_ctx* c, rb_streams8* out) {
+    if (!c || !out) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_fetch_compact: no scan result");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    const long long total = c->totals[0] + c->totals[1] + c->totals[2];
+    const int n = c->batch.n_contigs;
+    const int long_cap = 1 << 16;  // candidates of >= 65535 positions per stream and batch; more than this is an error
+    int rc = ensure(c, c->d_dst8, (size_t)std::max<long long>(total, 1) * 8);
+    if (rc) return rc;
+    rc = ensure(c, c->d_long, (size_t)3 * long_cap * 16 + 16);
+    if (rc) return rc;
+    rc = ensure_pinned(c, c->h_rec, c->h_rec_cap, (size_t)std::max<long long>(total, 1) * 8);
+    if (rc) return rc;
+    rc = ensure_pinned(c, c->h_off, c->h_off_cap, 3 * ((size_t)n + 1) * sizeof(long long));
+    if (rc) return rc;
+    rc = ensure_pinned(c, c->h_long, c->h_long_cap, (size_t)3 * long_cap * 16 + 16);
+    if (rc) return rc;
+    int* d_cnt = (int*)((char*)c->d_long.p + (size_t)3 * long_cap * 16);
+    RB_CUDA(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
+    launch_compact((const Rec*)c->d_dst.p, total, c->totals[0], c->totals[0] + c->totals[1], c->d_dst8.p, (long long*)c->d_long.p,
+                   long_cap, d_cnt, c->stream);
+    if (total > 0) RB_CUDA(c, cudaMemcpyAsync(c->h_rec, c->d_dst8.p, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (c->batch.n_buckets > 0)
+        RB_CUDA(c, cudaMemcpyAsync(c->h_off, c->d_contig_off.p, 3 * ((size_t)n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    else
+        memset(c->h_off, 0, 3 * ((size_t)n + 1) * sizeof(long long));
+    int* h_cnt = (int*)((char*)c->h_long + (size_t)3 * long_cap * 16);
+    RB_CUDA(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RB_CUDA(c, cudaGetLastError());
+    for (int s = 0; s < 3; ++s) {
+        if (h_cnt[s] > long_cap) return fail(c, RB_E_RANGE, "rb_fetch_compact: more than %d candidates of >= 65535 positions in stream %d; use rb_fetch", long_cap, s);
+        c->long_sorted[s].resize((size_t)h_cnt[s]);
+        if (h_cnt[s]) {
+            RB_CUDA(c, cudaMemcpy(c->long_sorted[s].data(), (char*)c->d_long.p + (size_t)s * long_cap * 16, (size_t)h_cnt[s] * 16, cudaMemcpyDeviceToHost));
+            std::sort(c->long_sorted[s].begin(), c->long_sorted[s].end(), [](const rb_long_end& a, const rb_long_end& b) { return a.index < b.index; });
+        }
+    }
+    out->n_contigs = n;
+    out->reserved = 0;
+    long long base = 0;
+    for (int s = 0; s < 3; ++s) {
+        out->rec[s] = (const rb_rec8*)c->h_rec + base;
+        out->contig_off[s] = (const int64_t*)c->h_off + (size_t)s * (n + 1);
+        out->n[s] = c->totals[s];
+        out->long_end[s] = c->long_sorted[s].data();
+        out->n_long[s] = (int64_t)c->long_sorted[s].size();
         base += c->totals[s];
     }
     return RB_OK;

@@ -560,6 +560,41 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     }
 }
 
+// 16-byte records -> 8-byte records (rb_rec8); candidates of 65535 positions or more go to a side list.
+// stream s occupies [sbase[s], sbase[s+1]) of both pools; long_cnt[s] counts the side-list entries of stream s.
+__global__ void __launch_bounds__(256) compact_kernel(const Rec* __restrict__ src, long long n, long long b1, long long b2,
+                                                      uint2* __restrict__ dst, long long* __restrict__ long_list, int long_cap,
+                                                      int* __restrict__ long_cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 r = *reinterpret_cast<const int4*>(src + i);
+    const int mlen = r.z & 0xFFFF, flags = (r.z >> 16) & 0xF;
+    uint2 o;
+    if (flags & REC_PSEUDO) {
+        o.x = (uint32_t)r.y;
+        o.y = (uint32_t)(mlen | (flags << 12)) << 16;
+    } else {
+        const int len = r.y - r.x;
+        o.x = (uint32_t)r.x;
+        o.y = (uint32_t)(len >= 0xFFFF ? 0xFFFF : len) | ((uint32_t)(mlen | (flags << 12)) << 16);
+        if (len >= 0xFFFF) {
+            const int s = i >= b2 ? 2 : (i >= b1 ? 1 : 0);
+            const int k = atomicAdd(long_cnt + s, 1);
+            if (k < long_cap) {
+                long_list[((long long)s * long_cap + k) * 2] = i - (s == 2 ? b2 : (s == 1 ? b1 : 0));
+                long_list[((long long)s * long_cap + k) * 2 + 1] = r.y;
+            }
+        }
+    }
+    dst[i] = o;
+}
+
+void launch_compact(const Rec* src, long long n, long long b1, long long b2, void* dst, long long* long_list, int long_cap,
+                    int* long_cnt, cudaStream_t st) {
+    if (n == 0) return;
+    compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, n, b1, b2, (uint2*)dst, long_list, long_cap, long_cnt);
+}
+
 void launch_merge_count(const DevBatch& b, cudaStream_t st) {
     if (b.n_buckets == 0) return;
     merge_count_kernel<<<(unsigned)b.n_merge_blocks, MERGE_BLOCK, 0, st>>>(b);

@@ -52,6 +52,9 @@ void launch_pack(const DevBatch& b, cudaStream_t st);
 void launch_scan(const DevBatch& b, cudaStream_t st);
 void launch_merge_count(const DevBatch& b, cudaStream_t st);   // M1 + M2
 void launch_merge_write(const DevBatch& b, cudaStream_t st);   // M3
+// 16-byte -> 8-byte records; long_list[s][k] = {index in stream s, end}, long_cnt[3]
+void launch_compact(const Rec* src, long long n, long long b1, long long b2, void* dst, long long* long_list, int long_cap,
+                    int* long_cnt, cudaStream_t st);
 // K5: seeds = int4 {contig, start, end, mlen}[n] (device), out = int2 {seq_len, longest_run}[n] (device)
 void launch_seed_filter(const DevBatch& b, const void* seeds, long long n, void* out, cudaStream_t st);
 // anchor planes A_s, s = s_lo .. s_lo+ns-1, of one contig: out[(s - s_lo) * nw + w]

@@ -13,9 +13,10 @@ from . import scan
 
 
 class ScanPipeline:
-    def __init__(self, min_mlen=2, max_mlen=100, device=0, depth=3, copy=False):
+    def __init__(self, min_mlen=2, max_mlen=100, device=0, depth=3, copy=False, compact=False):
         self.depth = depth
         self.copy = copy
+        self.compact = compact  # fetch 8-byte records (rb_fetch_compact): half the D2H traffic
         self.scanners = [scan.Scanner(min_mlen, max_mlen, device=device) for _ in range(depth)]
         self.pools = [ThreadPoolExecutor(max_workers=1) for _ in range(depth)]  # one host thread per context
         self.n = 0
@@ -23,7 +24,7 @@ class ScanPipeline:
     def _run(self, k, buf, lengths):
         sc = self.scanners[k]
         sc.load_flat(buf, lengths)
-        return sc.scan(copy=self.copy)
+        return sc.scan_compact(copy=self.copy) if self.compact else sc.scan(copy=self.copy)
 
     def submit_flat(self, buf, lengths):
         """buf: uint8 numpy array holding the contigs back to back (pinned for full-speed copies)."""

@@ -15,12 +15,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RIBBIT_SCAN_LIB", os.path.join(_HERE, "lib", "libribbit_scan.so"))  # override: experiments only
 
 REC_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("mlen", "<u2"), ("flags", "<u2"), ("time", "<i4")])
+REC8_DTYPE = np.dtype([("start", "<i4"), ("len", "<u2"), ("mf", "<u2")])
+LONG_DTYPE = np.dtype([("index", "<i8"), ("end", "<i8")])
 REC_DROPPED, REC_PSEUDO, REC_NOCOMMIT = 1, 2, 4
 STREAM_NAMES = ("perfect", "subst", "anchored")
 
 EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
            "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes",
-           "rb_measure_int_peak", "rb_get_anchor_planes")
+           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact")
 
 
 class RbParams(ctypes.Structure):
@@ -31,6 +33,12 @@ class RbParams(ctypes.Structure):
 class RbStreams(ctypes.Structure):
     _fields_ = [("n_contigs", ctypes.c_int32), ("reserved", ctypes.c_int32), ("rec", ctypes.c_void_p * 3),
                 ("contig_off", ctypes.c_void_p * 3), ("n", ctypes.c_int64 * 3)]
+
+
+class RbStreams8(ctypes.Structure):
+    _fields_ = [("n_contigs", ctypes.c_int32), ("reserved", ctypes.c_int32), ("rec", ctypes.c_void_p * 3),
+                ("contig_off", ctypes.c_void_p * 3), ("n", ctypes.c_int64 * 3), ("long_end", ctypes.c_void_p * 3),
+                ("n_long", ctypes.c_int64 * 3)]
 
 
 class RbTiming(ctypes.Structure):
@@ -77,6 +85,8 @@ def load_library(path=LIB_PATH):
     lib.rb_scan_device.argtypes = [ctypes.c_void_p]
     lib.rb_fetch.restype = ctypes.c_int
     lib.rb_fetch.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbStreams)]
+    lib.rb_fetch_compact.restype = ctypes.c_int
+    lib.rb_fetch_compact.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbStreams8)]
     lib.rb_scan.restype = ctypes.c_int
     lib.rb_scan.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbStreams)]
     lib.rb_counts.restype = ctypes.c_int
@@ -170,6 +180,27 @@ class Scanner:
         self._check(self.lib.rb_fetch(self.ctx, ctypes.byref(out)))
         return self._wrap(out, copy)
 
+    def fetch_compact(self, copy=True):
+        """The streams as 8-byte records (rb_rec8): {stream: (records, contig offsets, long-candidate list)}."""
+        out = RbStreams8()
+        self._check(self.lib.rb_fetch_compact(self.ctx, ctypes.byref(out)))
+        res = {}
+        n = out.n_contigs
+        for s in range(3):
+            cnt = out.n[s]
+            a = (np.ctypeslib.as_array(ctypes.cast(out.rec[s], ctypes.POINTER(ctypes.c_uint8)), shape=(cnt * 8,)).view(REC8_DTYPE)
+                 if cnt else np.zeros(0, dtype=REC8_DTYPE))
+            off = np.ctypeslib.as_array(ctypes.cast(out.contig_off[s], ctypes.POINTER(ctypes.c_int64)), shape=(n + 1,))
+            nl = out.n_long[s]
+            lg = (np.ctypeslib.as_array(ctypes.cast(out.long_end[s], ctypes.POINTER(ctypes.c_uint8)), shape=(nl * 16,)).view(LONG_DTYPE)
+                  if nl else np.zeros(0, dtype=LONG_DTYPE))
+            res[s] = (a.copy() if copy else a, off.copy() if copy else off, lg.copy())
+        return res
+
+    def scan_compact(self, copy=True):
+        self.scan_device()
+        return self.fetch_compact(copy)
+
     def scan(self, copy=True):
         out = RbStreams()
         self._check(self.lib.rb_scan(self.ctx, ctypes.byref(out)))
@@ -220,6 +251,20 @@ class Scanner:
         out = np.zeros((len(seeds), 2), dtype=np.int32)
         self._check(self.lib.rb_filter_seeds(self.ctx, seeds.ctypes.data, len(seeds), out.ctypes.data))
         return out
+
+
+def expand_compact(rec8, long_end):
+    """rb_rec8 array (+ its long-candidate list) -> rows (start, end, mlen, flags), the PSEUDO convention of rb_rec."""
+    start = rec8["start"].astype(np.int64)
+    end = start + rec8["len"].astype(np.int64)
+    if len(long_end):
+        end[long_end["index"]] = long_end["end"]
+    mlen = (rec8["mf"] & 0xFFF).astype(np.int64)
+    flags = (rec8["mf"] >> 12).astype(np.int64)
+    ps = (flags & REC_PSEUDO) != 0
+    end[ps] = start[ps]
+    start[ps] = -1
+    return np.stack([start, end, mlen, flags], axis=1)
 
 
 def contig_streams(res, contig):

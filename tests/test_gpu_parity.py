@@ -299,3 +299,25 @@ def test_python_cli_writes_kept_candidates(built, tmp_path):
             e = exp[s]
             e = e[(e[:, 3] & (scan.REC_DROPPED | scan.REC_PSEUDO)) == 0]
             assert mine == [tuple(x) for x in e[:, :3].tolist()]
+
+
+def test_compact_fetch_equals_full_fetch(built):
+    rng = np.random.default_rng(41)
+    long_rep = b"ACGGTCA" * 10000                                   # a 70 kb perfect repeat: candidates longer than 65535
+    contigs = [synth.fuzz_contig(rng, 30000, 0.002), synth.random_bases(rng, 3000).tobytes() + long_rep + synth.random_bases(rng, 3000).tobytes(),
+               b"", synth.fuzz_contig(rng, 900, 0.05)]
+    sc = scan.Scanner(2, 100)
+    sc.load(contigs)
+    full = sc.scan()
+    comp = sc.fetch_compact()
+    nlong = 0
+    for s in range(3):
+        a, off = full[s]
+        r8, off8, lg = comp[s]
+        assert (off == off8).all() and len(a) == len(r8)
+        rows = scan.expand_compact(r8, lg)
+        exp = np.stack([a["start"], a["end"], a["mlen"], a["flags"]], axis=1).astype(np.int64)
+        assert (rows == exp).all(), s
+        nlong += len(lg)
+    assert nlong > 0
+    sc.close()
