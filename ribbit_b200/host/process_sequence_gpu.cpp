@@ -15,7 +15,9 @@
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -68,6 +70,21 @@ rb_ctx *gpu_context() {
         g_gpu.m_lo = MINIMUM_MLEN; g_gpu.m_hi = MAXIMUM_MLEN;
     }
     return g_gpu.ctx;
+}
+
+// The planes of different shifts are independent: build them on several host cores (the reference is single-threaded,
+// but nothing here touches its globals). RIBBIT_HOST_THREADS overrides the thread count.
+template <class F>
+void parallel_for(int n, F body) {
+    const char *env = getenv("RIBBIT_HOST_THREADS");
+    int nt = env ? atoi(env) : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    nt = std::max(1, std::min(nt, n));
+    if (nt == 1) { for (int i = 0; i < n; ++i) body(i); return; }
+    std::atomic<int> next(0);
+    vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&] { for (int i = next++; i < n; i = next++) body(i); });
+    for (auto &th : pool) th.join();
 }
 
 // A plane given as 32-base words (bit i of word w = position 32w+i) -> the reference's bitset, whose bit index is
@@ -134,9 +151,13 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
             default: MATRIX.push_back(NULL); break;
         }
     }
-    vector<Bitset> lshift_xor_bsets;  // fasta_utils.cpp:117-122, word-parallel already in the reference
-    for (int i = MINIMUM_SHIFT; i <= MAXIMUM_SHIFT; i++)
-        lshift_xor_bsets.push_back(~(left_bset ^ (left_bset << (i))) & ~(right_bset ^ (right_bset << (i))));
+    // fasta_utils.cpp:117-122: one match plane per shift, word-parallel already in the reference; the planes are
+    // independent of each other, so they are built on all host cores
+    vector<Bitset> lshift_xor_bsets((size_t)NSHIFTS);
+    parallel_for(NSHIFTS, [&](int k) {
+        const int i = MINIMUM_SHIFT + k;
+        lshift_xor_bsets[(size_t)k] = ~(left_bset ^ (left_bset << (i))) & ~(right_bset ^ (right_bset << (i)));
+    });
 
     SeedList seed_positions_perfect, seed_positions_substut, seed_positions_anchored;
     const int bset_size = sequence_length;
@@ -174,16 +195,17 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     {
         vector<uint32_t> anchors((size_t)nw * NSHIFTS + 1);
         if (rb_get_anchor_planes(ctx, 0, MINIMUM_SHIFT, MAXIMUM_SHIFT, anchors.data()) != RB_OK) die("rb_get_anchor_planes", ctx);
-        vector<Bitset> lsxor_anchor_bsets;
-        for (int s = 0; s < NSHIFTS; s++) lsxor_anchor_bsets.push_back(to_bitset(anchors.data() + (size_t)s * nw, sequence_length));
+        vector<Bitset> lsxor_anchor_bsets((size_t)NSHIFTS);
+        parallel_for(NSHIFTS, [&](int s) { lsxor_anchor_bsets[(size_t)s] = to_bitset(anchors.data() + (size_t)s * nw, sequence_length); });
         // B_m = X_m | A_i for the shifts i within two of m (from 1 when m <= 2), written over plane m in ascending m:
         // planes m-2 and m-1 were already overwritten, but only their anchor planes are read (fasta_utils.cpp:146-160)
-        for (int m = MINIMUM_MLEN; m <= MAXIMUM_MLEN; ++m) {
+        parallel_for(NMOTIFS, [&](int k) {  // plane m reads its own match plane and anchor planes only
+            const int m = MINIMUM_MLEN + k;
             Bitset bm = lshift_xor_bsets[m - MINIMUM_SHIFT];
             for (int i = (m > 2) ? m - 2 : 1; i <= m + 2; ++i)
                 if (i != m) bm |= lsxor_anchor_bsets[i - MINIMUM_SHIFT];
             lshift_xor_bsets[m - MINIMUM_SHIFT] = bm;
-        }
+        });
     }
     cerr << "Generated anchored shift XORs!\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
 
