@@ -174,7 +174,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Gbp/s scanned (motifs 2-100)", "value": value, "unit": "Gbp/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (cores * args.ref_sample / 1e9) / value, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 bit planes", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args.bases), "sample": what},
         "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -308,7 +308,7 @@ def run_gpu(args):
         line = {
             "metric": "Gbp/s scanned (motifs 2-100)", "value": value, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit planes",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
             "config": {"workload": workload_name(L), "bases_per_gpu": L, "min_mlen": M_LO, "max_mlen": M_HI,
                        "l2": "flushed (512 MiB write) between timed steps", "timing": "CUDA events on the library stream, max over ranks",
