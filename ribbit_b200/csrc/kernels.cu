@@ -34,6 +34,29 @@ __global__ void __launch_bounds__(256) pack_kernel(DevBatch b) {
         const uint8_t* __restrict__ src = b.ascii + cg.ascii_off;
         unsigned long long nx = 0ull;  // bit i <-> position p0 - 7 + i
         uint32_t h = 0u, l = 0u;
+        if (w >= 1 && p0 + 32 <= cg.L && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0ull) {
+            // interior word of a 16-byte aligned contig: two uint4 loads (32 bases) + one uint2 (the 8 bases before),
+            // four bases at a time with byte-parallel arithmetic
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(src + p0));
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(src + p0 + 16));
+            const uint2 qh = __ldg(reinterpret_cast<const uint2*>(src + p0 - 8));
+            const uint32_t wd[10] = {qh.x, qh.y, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            uint32_t nn = 0u, nhist = 0u;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                const uint32_t y = wd[k] | 0x20202020u;  // fasta_utils.cpp:95-113: either case
+                // byte == 'a' / 'c' / 'g' / 't' -> 0xFF in that byte
+                const uint32_t acgt = (__vcmpeq4(y, 0x61616161u) | __vcmpeq4(y, 0x63636363u) | __vcmpeq4(y, 0x67676767u) |
+                                       __vcmpeq4(y, 0x74747474u)) & 0x01010101u;
+                // a=0x61 c=0x63 g=0x67 t=0x74: high code bit = bit 2, low code bit = bit 1 ^ bit 2
+                const uint32_t hb = (y >> 2) & acgt, lb = ((y >> 1) ^ (y >> 2)) & acgt, nb = acgt ^ 0x01010101u;
+                // one bit per byte -> 4 adjacent bits (byte 0 -> bit 0)
+                const uint32_t h4 = (hb * 0x10204080u) >> 28, l4 = (lb * 0x10204080u) >> 28, n4 = (nb * 0x10204080u) >> 28;
+                if (k < 2) nhist |= n4 << (4 * k);
+                else { h |= h4 << (4 * (k - 2)); l |= l4 << (4 * (k - 2)); nn |= n4 << (4 * (k - 2)); }
+            }
+            nx = ((unsigned long long)nn << 7) | (unsigned long long)(nhist >> 1);  // positions p0-7 .. p0+31
+        } else
 #pragma unroll
         for (int i = 0; i < 39; ++i) {
             const long long p = p0 - 7 + i;
