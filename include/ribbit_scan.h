@@ -169,6 +169,20 @@ typedef struct rb_seedinfo {
 } rb_seedinfo;
 int rb_filter_seeds(rb_ctx *ctx, const rb_seed *seeds, int64_t n, rb_seedinfo *out);
 
+/* K7: the row search of mostFrequentLongerMotif (parse_seed.cpp:153-256; the reference calls it for motif sizes > 10,
+ * parse_seed.cpp:388-390), batched on the device. Here a seed is given as the function's own arguments: start =
+ * seed_start, end = seed_start + seed_sequence_length (the N-truncated length rb_filter_seeds returns; the region
+ * [start, end) must not contain N, as in the reference), mlen = motif_length >= 3 (with
+ * smaller sizes the reference's unit walk, parse_seed.cpp:197-198, need not advance). Returns per seed the row the reference
+ * settles on (mmotif_index, parse_seed.cpp:241: the first row with the largest diagonal-match count, 0 when no row scores
+ * or the seed is shorter than the motif) and that count. The consensus motif is the mlen bases starting at row
+ * (parse_seed.cpp:246-253). */
+typedef struct rb_motifrow {
+    int32_t row;    /* mmotif_index */
+    int32_t count;  /* max_count */
+} rb_motifrow;
+int rb_motif_rows(rb_ctx *ctx, const rb_seed *seeds, int64_t n, rb_motifrow *out);
+
 /* Anchor planes A_s (generateAnchoredShiftXORs, parse_anchored_shiftxor.cpp:20-56: runs of 1s of the match plane X_s
  * with 3 <= length < 2s that are closed inside the scanned range) of contig c for shifts shift_lo..shift_hi, computed on
  * the device: out[(s - shift_lo) * ceil(L/32) + w], bit i of word w = position 32*w+i. The host side of the reference

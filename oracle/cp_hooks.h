@@ -10,6 +10,7 @@
 //   {1|2|3, start, end, mlen, 0}               CP1: top-level argument sequence of
 //                                              addSeedToSeedPositions{Perfect,Substitutions,Anchored}
 //   {11|12|13, start, end, mlen, rank}         CP2: the three lists after all passes
+//   {21, seed_start, seed_seq_len, mlen, row}  CP4: mostFrequentLongerMotif arguments and the row it chose
 #ifndef RB_CP_HOOKS_H
 #define RB_CP_HOOKS_H
 #ifdef __cplusplus

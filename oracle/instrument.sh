@@ -5,7 +5,8 @@
 # addSeedToSeedPositions* functions (those AFTER the scan functions start, so
 # recursive calls stay unlogged) are redirected to the RB_CP1_* macros of
 # cp_hooks.h, and a CP2 dump is added before the per-seed stage. Only the
-# binary is written into the repo tree (git-ignored oracle/_ref/).
+# binary is written into the repo tree (git-ignored oracle/_ref/). CP4: every call of mostFrequentLongerMotif
+# (parse_seed.cpp:153) logs its arguments and the row it chose (mmotif_index, parse_seed.cpp:241).
 set -e
 OUTBIN="$1"
 : "${REF:=/root/reference}" "${CXX:=g++}" "${CC:=gcc}"
@@ -19,6 +20,8 @@ sed -n '391p' "$T/parse_substitute_shiftxor.cpp" | grep -q 'processShiftXORswith
 sed -n '538p' "$T/parse_anchored_shiftxor.cpp"   | grep -q 'processShiftXORsAnchored'          || { echo "anchor A moved"; exit 1; }
 sed -n '74p'  "$T/fasta_utils.cpp"               | grep -q 'START_TIME = time(0)'              || { echo "anchor F moved"; exit 1; }
 sed -n '170p' "$T/fasta_utils.cpp"               | grep -q 'considering indels'                || { echo "anchor F2 moved"; exit 1; }
+sed -n '245p' "$T/parse_seed.cpp"                | grep -q 'return mmotif_index'               || { echo "anchor M moved"; exit 1; }
+sed -i '245a rb_cp_rec(21, seed_start, seed_sequence_length, motif_length, mmotif_index);' "$T/parse_seed.cpp"
 sed -i '147,$ s/addSeedToSeedPositionsPerfect(/RB_CP1_P(/'        "$T/parse_perfect_shiftxor.cpp"
 sed -i '392,$ s/addSeedToSeedPositionsSubstitutions(/RB_CP1_S(/'  "$T/parse_substitute_shiftxor.cpp"
 sed -i '539,$ s/addSeedToSeedPositionsAnchored(/RB_CP1_A(/'       "$T/parse_anchored_shiftxor.cpp"

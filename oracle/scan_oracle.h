@@ -49,6 +49,9 @@ void rbo_anchored_plane(const char *seq, int64_t L, int min_mlen, int max_mlen, 
 
 void rbo_free(void *p);
 
+/* oracle/motif_oracle.c: row search of mostFrequentLongerMotif (parse_seed.cpp:153-256); returns mmotif_index. */
+int32_t rbo_motif_row(const char *seq, int64_t L, int32_t seed_start, int32_t seed_len, int32_t m, int32_t *best);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,7 @@ struct rb_ctx {
     const void* ascii_dev_ext = nullptr;
 
     DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
-        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long;
+        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys;
     DevBatch batch{};
 
     // pinned host results
@@ -283,7 +283,7 @@ void rb_destroy(rb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_chunks,
                       &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_raw, &c->d_counters,
-                      &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long};
+                      &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long, &c->d_mitems, &c->d_mkeys};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     if (c->h_off) cudaFreeHost(c->h_off);
@@ -551,6 +551,43 @@ int rb_filter_seeds(rb_ctx* c, const rb_seed* seeds, int64_t n, rb_seedinfo* out
     RB_CUDA(c, cudaMemcpyAsync(out, c->d_seedinfo.p, (size_t)n * sizeof(rb_seedinfo), cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(c, cudaStreamSynchronize(c->stream));
     RB_CUDA(c, cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_motif_rows(rb_ctx* c, const rb_seed* seeds, int64_t n, rb_motifrow* out) {
+    if (!c || n < 0 || (n > 0 && (!seeds || !out))) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_motif_rows: planes exist after rb_scan_device");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    std::vector<int2> items;
+    for (int64_t i = 0; i < n; ++i) {
+        const rb_seed& s = seeds[i];
+        if (s.contig < 0 || s.contig >= c->batch.n_contigs || s.mlen < 3 || s.start < 0 || s.end < s.start ||
+            s.end > c->contigs[s.contig].L)
+            return fail(c, RB_E_ARG, "rb_motif_rows: seed %lld out of range", (long long)i);
+        const int rows = s.end - s.start - s.mlen + 1;  // parse_seed.cpp:179
+        for (int r = 0; r < rows; r += MOTIF_SLAB) items.push_back(make_int2((int)i, r));
+        if (items.size() > 0x7FFFFFFFull) return fail(c, RB_E_RANGE, "rb_motif_rows: more than 2^31 row slabs in one call");
+    }
+    if (n == 0) return RB_OK;
+    int rc = ensure(c, c->d_seeds, (size_t)n * sizeof(rb_seed));
+    if (rc) return rc;
+    rc = ensure(c, c->d_mkeys, (size_t)n * sizeof(unsigned long long));
+    if (rc) return rc;
+    rc = ensure(c, c->d_mitems, items.size() * sizeof(int2));
+    if (rc) return rc;
+    std::vector<unsigned long long> keys((size_t)n);
+    RB_CUDA(c, cudaMemcpyAsync(c->d_seeds.p, seeds, (size_t)n * sizeof(rb_seed), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(c, cudaMemcpyAsync(c->d_mitems.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(c, cudaMemsetAsync(c->d_mkeys.p, 0, (size_t)n * sizeof(unsigned long long), c->stream));
+    launch_motif_rows(c->batch, c->d_seeds.p, c->d_mitems.p, (long long)items.size(), c->d_mkeys.p, c->stream);
+    RB_CUDA(c, cudaGetLastError());
+    RB_CUDA(c, cudaMemcpyAsync(keys.data(), c->d_mkeys.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        const unsigned long long k = keys[(size_t)i];
+        out[i].count = (int32_t)(k >> 32);
+        out[i].row = k ? (int32_t)(0x7FFFFFFF - (uint32_t)(k & 0xFFFFFFFFull)) : 0;
+    }
     return RB_OK;
 }
 

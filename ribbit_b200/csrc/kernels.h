@@ -57,6 +57,10 @@ void launch_compact(const Rec* src, long long n, long long b1, long long b2, voi
                     int* long_cnt, cudaStream_t st);
 // K5: seeds = int4 {contig, start, end, mlen}[n] (device), out = int2 {seq_len, longest_run}[n] (device)
 void launch_seed_filter(const DevBatch& b, const void* seeds, long long n, void* out, cudaStream_t st);
+// K7 (motif_kernels.cu): items = int2 {seed index, first row of the slab - seed_start}[n_items], keys[n seeds] zeroed by the
+// caller; afterwards keys[i] = count << 32 | (0x7FFFFFFF - row) of the seed's best row, 0 if no row scores
+static const int MOTIF_SLAB = 256;
+void launch_motif_rows(const DevBatch& b, const void* seeds, const void* items, long long n_items, void* keys, cudaStream_t st);
 // anchor planes A_s, s = s_lo .. s_lo+ns-1, of one contig: out[(s - s_lo) * nw + w]
 void launch_anchor_planes(const PlaneWord* cw, int L, int nw, int s_lo, int ns, uint32_t* out, cudaStream_t st);
 // LOP3 + SHF warp-lane operations per second the device sustains (integer-pipe roofline denominator)

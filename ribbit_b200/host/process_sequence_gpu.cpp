@@ -19,8 +19,10 @@
 #include <string>
 #include <thread>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
+#include "bitseq_utils.h"
 #include "fasta_utils.h"
 #include "global_variables.h"
 #include "parse_seed.h"
@@ -114,7 +116,44 @@ Bitset to_bitset(const uint32_t *w, long L) {
     return b;
 }
 
+#ifndef RIBBIT_HOST_MOTIF
+// K7: rows chosen by the consensus-motif search (rb_motif_rows) for the top-level seeds of the current contig, computed in
+// one batch before the per-seed walk. key = seed_start | mlen << 32; value = {seed_sequence_length, row}.
+struct MotifRows {
+    std::unordered_map<uint64_t, std::pair<int, int>> rows;
+    long hits = 0, misses = 0;
+    static uint64_t key(int start, int mlen) { return (uint64_t)(uint32_t)start | ((uint64_t)(uint32_t)mlen << 32); }
+} g_motif;
+#endif
+
 }  // namespace
+
+#ifndef RIBBIT_HOST_MOTIF
+// Replaces the reference's mostFrequentLongerMotif (parse_seed.cpp:153-256; ribbit_b200/host/Makefile renames that
+// definition, so processSeed's call at parse_seed.cpp:389 binds here): the row search runs on the GPU — batched ahead for
+// the top-level seeds, one rb_motif_rows call for the flank seeds processSeed recurses into (parse_seed.cpp:443-463) —
+// and the motif is read off the code planes at the chosen row (parse_seed.cpp:246-253).
+uint256_t mostFrequentLongerMotif(Bitset &left_bset, Bitset &right_bset, int &seed_start, int &seed_sequence_length,
+                                  int &motif_length, int &sequence_length, vector<Bitset *> &) {
+    int row;
+    auto hit = g_motif.rows.find(MotifRows::key(seed_start, motif_length));
+    if (hit != g_motif.rows.end() && hit->second.first == seed_sequence_length) {
+        row = hit->second.second; ++g_motif.hits;
+    } else {
+        const rb_seed sd = {0, seed_start, seed_start + seed_sequence_length, motif_length};
+        rb_motifrow r;
+        if (rb_motif_rows(g_gpu.ctx, &sd, 1, &r) != RB_OK) die("rb_motif_rows", g_gpu.ctx);
+        row = r.row; ++g_motif.misses;
+    }
+    uint256_t unit = 0;
+    for (int j = row; j < row + motif_length; ++j) {
+        const size_t b = (size_t)(sequence_length - 1 - j);
+        unit <<= 2;
+        unit |= uint256_t((left_bset[b] ? 2 : 0) | (right_bset[b] ? 1 : 0));
+    }
+    return unit;
+}
+#endif
 
 void processSequence(string &sequence_id, string &sequence, int window_length, int window_bitcount_threshold, int anchor_size,
                      int continuous_ones_threshold, ostream &out) {
@@ -137,9 +176,11 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     if (rb_get_planes(ctx, 0, hi.data(), lo.data(), nn.data()) != RB_OK) die("rb_get_planes", ctx);
     Bitset left_bset = to_bitset(hi.data(), sequence_length), right_bset = to_bitset(lo.data(), sequence_length),
            N_bset = to_bitset(nn.data(), sequence_length);
-    // one-hot planes + per-base pointers: only the per-seed stage reads them (fasta_utils.cpp:83-115)
-    Bitset A(sequence_length, 0ull), T(sequence_length, 0ull), G(sequence_length, 0ull), C(sequence_length, 0ull);
+    // one-hot planes + per-base pointers (fasta_utils.cpp:83-115): only mostFrequentLongerMotif reads them, which runs on
+    // the GPU from the packed planes (K7) — they are built only when the host version is compiled in
     vector<Bitset *> MATRIX;
+#ifdef RIBBIT_HOST_MOTIF
+    Bitset A(sequence_length, 0ull), T(sequence_length, 0ull), G(sequence_length, 0ull), C(sequence_length, 0ull);
     MATRIX.reserve((size_t)sequence_length);
     for (int i = 0; i < sequence_length; i++) {
         const int bidx = (sequence_length - 1) - i;
@@ -151,6 +192,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
             default: MATRIX.push_back(NULL); break;
         }
     }
+#endif
     // fasta_utils.cpp:117-122: one match plane per shift, word-parallel already in the reference; the planes are
     // independent of each other, so they are built on all host cores
     vector<Bitset> lshift_xor_bsets((size_t)NSHIFTS);
@@ -278,6 +320,22 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     vector<rb_seedinfo> info(todo.size());
     const bool use_filter = !getenv("RIBBIT_NO_SEED_FILTER");
     if (use_filter && !todo.empty() && rb_filter_seeds(ctx, todo.data(), (int64_t)todo.size(), info.data()) != RB_OK) die("rb_filter_seeds", ctx);
+#ifndef RIBBIT_HOST_MOTIF
+    // K7: processSeed calls mostFrequentLongerMotif(seed_start, N-truncated seed length, mlen) for every seed with mlen > 10
+    // that passes the gate (parse_seed.cpp:344-390) — all of them in one batch
+    g_motif.rows.clear();
+    if (use_filter) {
+        vector<rb_seed> mseeds;
+        for (size_t k = 0; k < todo.size(); ++k)
+            if (todo[k].mlen > 10 && info[k].longest_run >= continuous_ones_threshold)
+                mseeds.push_back(rb_seed{0, todo[k].start, todo[k].start + info[k].seq_len, todo[k].mlen});
+        vector<rb_motifrow> mrows(mseeds.size());
+        if (!mseeds.empty() && rb_motif_rows(ctx, mseeds.data(), (int64_t)mseeds.size(), mrows.data()) != RB_OK) die("rb_motif_rows", ctx);
+        g_motif.rows.reserve(mseeds.size() * 2);
+        for (size_t k = 0; k < mseeds.size(); ++k)
+            g_motif.rows.emplace(MotifRows::key(mseeds[k].start, mseeds[k].mlen), std::make_pair(mseeds[k].end - mseeds[k].start, mrows[k].row));
+    }
+#endif
     for (size_t k = 0; k < todo.size(); ++k) {
         if (use_filter && info[k].longest_run < continuous_ones_threshold) continue;
         int mlen = todo[k].mlen, rank = todo_rank[k];
@@ -290,5 +348,8 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
             processSeed(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset, right_bset,
                         N_bset, continuous_ones_threshold, out, MATRIX, aligner, filter, alignment);
     }
+#ifndef RIBBIT_HOST_MOTIF
+    if (getenv("RIBBIT_VERBOSE")) cerr << "K7 motif rows: " << g_motif.hits << " from the batch, " << g_motif.misses << " single calls\n";
+#endif
     cerr << "Total number of seeds that are processed for alignment: " << processed_seeds << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
 }

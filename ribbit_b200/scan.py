@@ -22,7 +22,7 @@ STREAM_NAMES = ("perfect", "subst", "anchored")
 
 EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
            "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes",
-           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact")
+           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact", "rb_motif_rows")
 
 
 class RbParams(ctypes.Structure):
@@ -95,6 +95,8 @@ def load_library(path=LIB_PATH):
     lib.rb_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbTiming)]
     lib.rb_filter_seeds.restype = ctypes.c_int
     lib.rb_filter_seeds.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.rb_motif_rows.restype = ctypes.c_int
+    lib.rb_motif_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.rb_measure_int_peak.restype = ctypes.c_int
     lib.rb_measure_int_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
     lib.rb_get_anchor_planes.restype = ctypes.c_int
@@ -250,6 +252,14 @@ class Scanner:
         seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 4)
         out = np.zeros((len(seeds), 2), dtype=np.int32)
         self._check(self.lib.rb_filter_seeds(self.ctx, seeds.ctypes.data, len(seeds), out.ctypes.data))
+        return out
+
+    def motif_rows(self, seeds):
+        """K7, the row search of mostFrequentLongerMotif (parse_seed.cpp:153-256). seeds: (n,4) int32 rows
+        (contig, seed_start, seed_start + seed_sequence_length, mlen) -> (n,2) int32 rows (row, count)."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 4)
+        out = np.zeros((len(seeds), 2), dtype=np.int32)
+        self._check(self.lib.rb_motif_rows(self.ctx, seeds.ctypes.data, len(seeds), out.ctypes.data))
         return out
 
 

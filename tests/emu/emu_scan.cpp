@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "layout.h"
+#include "motif_core.h"
 #include "merge_core.h"
 #include "scan_core.h"
 
@@ -213,4 +214,25 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
 }
 
 void emu_free(void* p) { free(p); }
+
+// K7 on the CPU: the kernel's per-row scoring (motif_core.h) and its reduction rule (largest count, then smallest row; no
+// scoring row -> 0). seeds = n x {start, end, mlen}; out = n x {row, count}.
+int emu_motif_rows(const char* seq, int64_t L, const int32_t* seeds, int64_t n, int32_t* out) {
+    std::vector<PlaneWord> planes;
+    pack(seq, L, 8, planes);
+    const PlaneWord* cw = planes.data() + 1;
+    const int nw = (int)((L + 31) / 32);
+    for (int64_t i = 0; i < n; ++i) {
+        const int start = seeds[3 * i], end = seeds[3 * i + 1], m = seeds[3 * i + 2];
+        unsigned long long best = 0;
+        for (int row = start; row <= end - m; ++row) {
+            const int sc = motif_row_score(cw, nw, start, end, m, row);
+            const unsigned long long key = ((unsigned long long)(uint32_t)sc << 32) | (uint32_t)(0x7FFFFFFF - row);
+            if (key > best) best = key;
+        }
+        out[2 * i + 1] = (int32_t)(best >> 32);
+        out[2 * i] = (best >> 32) ? (int32_t)(0x7FFFFFFF - (uint32_t)(best & 0xFFFFFFFFull)) : 0;
+    }
+    return 0;
+}
 }

@@ -18,6 +18,7 @@ def lib():
                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
                                   ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         _lib.emu_free.argtypes = [ctypes.c_void_p]
+        _lib.emu_motif_rows.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     return _lib
 
 
@@ -42,3 +43,11 @@ def emu_streams(seq: bytes, m_lo: int, m_hi: int, chunk_words: int = 1 << 30, wa
         L.emu_free(out[s])
         res[s + 1] = rows
     return res, rs.value
+
+
+def emu_motif_rows(seq: bytes, seeds):
+    """K7 lane logic on the CPU. seeds: (n,3) rows (seed_start, seed_end, mlen) -> (n,2) rows (row, count)."""
+    sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int32).reshape(-1, 3))
+    out = np.zeros((len(sd), 2), np.int32)
+    lib().emu_motif_rows(seq, len(seq), sd.ctypes.data, len(sd), out.ctypes.data)
+    return out

@@ -35,8 +35,8 @@ def build_port():
 def port():
     global _lib
     if _lib is None:
-        if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(
-                os.path.join(ORACLE_DIR, "scan_oracle.c")):
+        if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < max(
+                os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("scan_oracle.c", "motif_oracle.c")):
             build_port()
         lib = ctypes.CDLL(PORT_SO)
         lib.rbo_scan.restype = ctypes.c_int64
@@ -51,6 +51,9 @@ def port():
         lib.rbo_anchored_plane.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
         lib.rbo_free.argtypes = [ctypes.c_void_p]
+        lib.rbo_motif_row.restype = ctypes.c_int32
+        lib.rbo_motif_row.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.POINTER(ctypes.c_int32)]
         _lib = lib
     return _lib
 
@@ -91,13 +94,22 @@ def anchored_plane(seq: bytes, m_lo: int, m_hi: int, m: int, p0: int, p1: int) -
     return out[:p1 - p0]
 
 
+def motif_row(seq: bytes, seed_start: int, seed_len: int, m: int):
+    """(row, count) of the oracle's mostFrequentLongerMotif row search."""
+    lib = port()
+    best = ctypes.c_int32(0)
+    row = lib.rbo_motif_row(seq, len(seq), seed_start, seed_len, m, ctypes.byref(best))
+    return int(row), int(best.value)
+
+
 def have_ref() -> bool:
     return os.access(REF_CP_BIN, os.X_OK) and os.access(REF_BIN, os.X_OK)
 
 
 def ref_cp(fasta_path: str, args=(), stop_after_cp2=False, timeout=3600):
     """Run the instrumented reference. Returns (contigs, bed_bytes, returncode) where contigs is a list of
-    dicts {L, cp1: (n,4) int32 rows (stream,start,end,mlen), cp2: (n,5) rows (list,start,end,mlen,rank)}."""
+    dicts {L, cp1: (n,4) int32 rows (stream,start,end,mlen), cp2: (n,5) rows (list,start,end,mlen,rank),
+    cp4: (n,4) rows (seed_start, seed_seq_len, mlen, row) of every mostFrequentLongerMotif call}."""
     with tempfile.TemporaryDirectory() as td:
         cp = os.path.join(td, "cp.bin")
         bed = os.path.join(td, "out.bed")
@@ -114,9 +126,10 @@ def ref_cp(fasta_path: str, args=(), stop_after_cp2=False, timeout=3600):
             e = starts[i + 1] if i + 1 < len(starts) else len(raw)
             blk = raw[s + 1:e]
             cp1 = blk[(blk[:, 0] >= 1) & (blk[:, 0] <= 3)][:, :4]
-            cp2 = blk[blk[:, 0] >= 11].copy()
+            cp2 = blk[(blk[:, 0] >= 11) & (blk[:, 0] <= 13)].copy()
             cp2[:, 0] -= 10
-            contigs.append({"L": int(raw[s, 2]), "cp1": cp1, "cp2": cp2})
+            cp4 = blk[blk[:, 0] == 21][:, 1:]
+            contigs.append({"L": int(raw[s, 2]), "cp1": cp1, "cp2": cp2, "cp4": cp4})
         bed_bytes = open(bed, "rb").read() if os.path.exists(bed) else b""
         return contigs, bed_bytes, r.returncode
 
