@@ -112,6 +112,22 @@ int rb_load_contigs(rb_ctx *ctx, const char *ascii, const int64_t *offsets, cons
  * next load. Used when the sequence is already resident in HBM. */
 int rb_load_contigs_device(rb_ctx *ctx, const void *ascii_dev, const int64_t *offsets, const int32_t *lengths, int32_t n);
 
+/* FASTA text -> contigs, parsed on the device (K0). Replaces the reference's reader loop ribbit.cpp:269-280 + the pack
+ * loop: `text` (host memory, nbytes) is copied to the device as it is; lines whose first byte is '>' are headers, every
+ * other line is sequence and is appended verbatim ('\n' is the only separator: a '\r' stays and becomes an N base, as in
+ * the reference). Records follow the reference's quirks: a header closes the record in front of it only if that record
+ * has sequence (an empty record's name is simply replaced), the text in front of the first header is an unnamed record,
+ * and the last record is produced even when empty (ribbit.cpp:280 calls processSequence unconditionally). The records
+ * become the loaded contigs (as after rb_load_contigs); rb_fasta_records returns, per record, where its name sits in
+ * `text` (the bytes between '>' and the first ' ' or the end of the line, ribbit.cpp:275; name_off = -1: unnamed). */
+typedef struct rb_fasta_record {
+    int64_t name_off;
+    int32_t name_len;
+    int32_t length;  /* bases */
+} rb_fasta_record;
+int rb_load_fasta(rb_ctx *ctx, const char *text, int64_t nbytes, int32_t *n_records);
+int rb_fasta_records(rb_ctx *ctx, rb_fasta_record *out, int32_t capacity);
+
 /* Runs pack + scan + ordered compaction on the device; results stay in device memory. */
 int rb_scan_device(rb_ctx *ctx);
 

@@ -6,7 +6,10 @@ Writes one row per candidate: contig, stream (P|S|A), start, end, mlen, flags, t
 that reach the consumer's length cutoff (flags 0 / NOCOMMIT); --all adds the DROPPED and PSEUDO bookkeeping records.
 For BED output use the drop-in program baseline/_ref/ribbit_gpu."""
 import argparse
+import os
 import sys
+
+import numpy as np
 
 from . import fasta, scan
 
@@ -24,15 +27,22 @@ def main(argv=None):
     sp.add_argument("--batch-bases", type=int, default=400_000_000, help="bases per GPU batch")
     args = ap.parse_args(argv)
 
-    names, seqs = fasta.read_fasta(args.input_file)
     out = sys.stdout if args.output_file == "-" else open(args.output_file, "w")
     sc = scan.Scanner(args.min_motif_length, args.max_motif_length, device=args.device)
+    whole = os.path.getsize(args.input_file) <= args.batch_bases
+    if whole:   # one batch: the file goes to the device as it is and is parsed there (rb_load_fasta)
+        names, lengths = sc.load_fasta(np.fromfile(args.input_file, dtype=np.uint8))
+        seqs = [None] * len(names)
+    else:       # several batches: records are cut on the host (same reader semantics, ribbit.cpp:269-280)
+        names, seqs = fasta.read_fasta(args.input_file)
+        lengths = [len(s) for s in seqs]
     i = 0
     while i < len(seqs):
         j, tot = i, 0
-        while j < len(seqs) and (j == i or tot + len(seqs[j]) <= args.batch_bases):
-            tot += len(seqs[j]); j += 1
-        sc.load(seqs[i:j])
+        while j < len(seqs) and (j == i or whole or tot + lengths[j] <= args.batch_bases):
+            tot += lengths[j]; j += 1
+        if not whole:
+            sc.load(seqs[i:j])
         res = sc.scan(copy=False)
         for c in range(i, j):
             for s, tag in enumerate("PSA"):

@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "lib", "libribbit_scan.so")
 EMU = os.path.join(ROOT, "tests", "emu", "libemu.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared"]
-CUDA_SOURCES = ["kernels.cu", "motif_kernels.cu", "api.cu"]
+CUDA_SOURCES = ["kernels.cu", "motif_kernels.cu", "fasta_kernels.cu", "api.cu"]
 
 
 def _newer(target, deps):

@@ -48,7 +48,7 @@ struct rb_ctx {
     const void* ascii_dev_ext = nullptr;
 
     DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
-        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys;
+        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys, d_text, d_ftiles, d_finfo, d_ftot, d_hpos, d_hseq;
     DevBatch batch{};
 
     // pinned host results
@@ -62,6 +62,7 @@ struct rb_ctx {
     long long* h_small = nullptr;  // pinned: totals[3], counters[2]
     long long totals[3] = {0, 0, 0};
     rb_timing timing{};
+    std::vector<rb_fasta_record> fasta_records;
 };
 
 namespace {
@@ -283,7 +284,8 @@ void rb_destroy(rb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_chunks,
                       &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_raw, &c->d_counters,
-                      &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long, &c->d_mitems, &c->d_mkeys};
+                      &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long, &c->d_mitems, &c->d_mkeys,
+                      &c->d_text, &c->d_ftiles, &c->d_finfo, &c->d_ftot, &c->d_hpos, &c->d_hseq};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     if (c->h_off) cudaFreeHost(c->h_off);
@@ -321,6 +323,72 @@ int rb_load_contigs_device(rb_ctx* c, const void* ascii_dev, const int64_t* offs
     rc = finish_load(c, ascii_dev, n);
     if (rc) return rc;
     RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RB_OK;
+}
+
+int rb_load_fasta(rb_ctx* c, const char* text, int64_t nbytes, int32_t* n_records) {
+    if (!c) return RB_E_ARG;
+    if (nbytes < 0 || (nbytes > 0 && !text)) return fail(c, RB_E_ARG, "rb_load_fasta: null argument");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const long long nt = fasta_tiles(nbytes);
+    int rc;
+    if ((rc = ensure(c, c->d_text, (size_t)nbytes + 64))) return rc;
+    if ((rc = ensure(c, c->d_ftiles, (size_t)std::max<long long>(nt, 1) * sizeof(int4)))) return rc;
+    if ((rc = ensure(c, c->d_finfo, (size_t)std::max<long long>(nt, 1) * sizeof(longlong2)))) return rc;
+    if ((rc = ensure(c, c->d_ftot, 2 * sizeof(long long)))) return rc;
+    if (nbytes > 0) RB_CUDA(c, cudaMemcpyAsync(c->d_text.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+    launch_fasta_count(c->d_text.p, nbytes, c->d_ftiles.p, c->d_finfo.p, (long long*)c->d_ftot.p, st);
+    RB_CUDA(c, cudaGetLastError());
+    RB_CUDA(c, cudaMemcpyAsync(c->h_small, c->d_ftot.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(c, cudaStreamSynchronize(st));
+    const long long n_seq = c->h_small[0], n_hdr = c->h_small[1];
+    if (n_hdr + 1 > 0x7FFFFFFFll) return fail(c, RB_E_RANGE, "rb_load_fasta: %lld records", n_hdr + 1);
+    if ((rc = ensure(c, c->d_ascii, (size_t)n_seq + 64))) return rc;
+    if ((rc = ensure(c, c->d_hpos, (size_t)std::max<long long>(n_hdr, 1) * sizeof(long long)))) return rc;
+    if ((rc = ensure(c, c->d_hseq, (size_t)std::max<long long>(n_hdr, 1) * sizeof(long long)))) return rc;
+    launch_fasta_strip(c->d_text.p, nbytes, c->d_finfo.p, c->d_ascii.p, (long long*)c->d_hpos.p, (long long*)c->d_hseq.p, st);
+    RB_CUDA(c, cudaGetLastError());
+    std::vector<long long> hpos((size_t)n_hdr), hseq((size_t)n_hdr);
+    if (n_hdr > 0) {
+        RB_CUDA(c, cudaMemcpyAsync(hpos.data(), c->d_hpos.p, (size_t)n_hdr * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(c, cudaMemcpyAsync(hseq.data(), c->d_hseq.p, (size_t)n_hdr * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    RB_CUDA(c, cudaStreamSynchronize(st));
+    // segment j = the sequence between header j-1 (none for j = 0) and header j; ribbit.cpp:271-279: a segment is a record
+    // if it has sequence, the last one always
+    c->fasta_records.clear();
+    std::vector<int64_t> offsets;
+    std::vector<int32_t> lengths;
+    for (long long j = 0; j <= n_hdr; ++j) {
+        const long long from = j == 0 ? 0 : hseq[(size_t)j - 1], to = j == n_hdr ? n_seq : hseq[(size_t)j];
+        if (to == from && j != n_hdr) continue;
+        if (to - from > 0x7FFFFFFFll - 4096) return fail(c, RB_E_RANGE, "rb_load_fasta: record %lld has %lld bases", j, to - from);
+        rb_fasta_record r;
+        r.name_off = -1; r.name_len = 0; r.length = (int32_t)(to - from);
+        if (j > 0) {
+            const long long p0 = hpos[(size_t)j - 1] + 1;
+            long long p = p0;
+            while (p < nbytes && text[p] != ' ' && text[p] != '\n') ++p;
+            r.name_off = p0; r.name_len = (int32_t)std::min<long long>(p - p0, 0x7FFFFFFF);
+        }
+        c->fasta_records.push_back(r);
+        offsets.push_back(from);
+        lengths.push_back(r.length);
+    }
+    const int32_t n = (int32_t)lengths.size();
+    if ((rc = build_geometry(c, offsets.data(), lengths.data(), n))) return rc;
+    c->ascii_external = false;
+    if ((rc = finish_load(c, c->d_ascii.p, n))) return rc;
+    RB_CUDA(c, cudaStreamSynchronize(st));
+    if (n_records) *n_records = n;
+    return RB_OK;
+}
+
+int rb_fasta_records(rb_ctx* c, rb_fasta_record* out, int32_t capacity) {
+    if (!c || capacity < 0 || (capacity > 0 && !out)) return RB_E_ARG;
+    if ((size_t)capacity < c->fasta_records.size()) return fail(c, RB_E_ARG, "rb_fasta_records: %zu records, capacity %d", c->fasta_records.size(), capacity);
+    for (size_t i = 0; i < c->fasta_records.size(); ++i) out[i] = c->fasta_records[i];
     return RB_OK;
 }
 

@@ -1,0 +1,249 @@
+// ribbit-b200: K0 — FASTA text -> contig bases on the device. Reference reader: the getline loop
+// ribbit.cpp:269-280 — a line whose FIRST byte is '>' is a header, every other line is appended verbatim (so a '\r'
+// or a '>' inside a line stay in the sequence and become N bases later), '\n' is the only separator.
+//
+// HBM-bound byte work in three passes over 4 KiB tiles (one block of 256 threads, 16 bytes per thread):
+//   fasta_tile_kernel   per tile: sequence bytes before the first control byte (their line type is decided by earlier
+//                       tiles), sequence bytes after it, header count, line type at the tile's end
+//   fasta_scan_kernel   one block: line type at every tile's start, exclusive prefixes of sequence bytes and headers
+//   fasta_strip_kernel  per tile: sequence bytes staged in shared memory at their rank, then written out coalesced;
+//                       per header: its offset in the text and the number of sequence bytes in front of it
+// A control byte is '\n' (the next line is sequence until proven otherwise) or a '>' that follows a '\n' / starts the text.
+#include "kernels.h"
+
+namespace rb {
+
+namespace {
+
+constexpr int FT_THREADS = 256;
+constexpr int FT_PER = 16;
+constexpr int FT_TILE = FT_THREADS * FT_PER;  // 4096 bytes
+
+enum : int { LT_SEQ = 0, LT_HDR = 1, LT_NONE = 2 };
+
+struct Bytes16 {
+    uint8_t b[FT_PER];
+    uint8_t prev;  // byte in front of b[0] ('\n' in front of the text)
+    int n;         // valid bytes
+};
+
+__device__ __forceinline__ Bytes16 load16(const uint8_t* __restrict__ text, long long nbytes, long long at) {
+    Bytes16 r;
+    r.n = (int)max(0ll, min((long long)FT_PER, nbytes - at));
+    if (r.n == FT_PER && ((reinterpret_cast<uintptr_t>(text + at) & 15) == 0)) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + at));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < FT_PER; ++i) r.b[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+    } else {
+#pragma unroll
+        for (int i = 0; i < FT_PER; ++i) r.b[i] = (i < r.n) ? __ldg(text + at + i) : (uint8_t)'\n';
+    }
+    r.prev = (at > 0 && at <= nbytes) ? __ldg(text + at - 1) : (uint8_t)'\n';
+    return r;
+}
+
+// inclusive max-scan over the block (values >= -1); returns the EXCLUSIVE result for this thread, *total = block max
+__device__ __forceinline__ int block_excl_max(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x = max(x, y);
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int before = -1, all = -1;
+#pragma unroll
+    for (int w = 0; w < FT_THREADS / 32; ++w) {
+        const int t = s_warp[w];
+        if (w < warp) before = max(before, t);
+        all = max(all, t);
+    }
+    __syncthreads();
+    int ex = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+    if (lane == 0) ex = -1;
+    if (total) *total = all;
+    return max(before, ex);
+}
+
+// exclusive sum-scan over the block; *total = block sum
+__device__ __forceinline__ int block_excl_sum(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < FT_THREADS / 32; ++w) {
+        const int t = s_warp[w];
+        if (w < warp) before += t;
+        all += t;
+    }
+    __syncthreads();
+    if (total) *total = all;
+    return before + x - v;
+}
+
+// The thread's last control byte as (index in tile) * 2 + line type it starts, -1 if none.
+__device__ __forceinline__ int last_control(const Bytes16& d, int first_index) {
+    int last = -1;
+    uint8_t prev = d.prev;
+#pragma unroll
+    for (int i = 0; i < FT_PER; ++i) {
+        if (i < d.n) {
+            if (d.b[i] == '\n') last = (first_index + i) * 2 + LT_SEQ;
+            else if (d.b[i] == '>' && prev == '\n') last = (first_index + i) * 2 + LT_HDR;
+        }
+        prev = d.b[i];
+    }
+    return last;
+}
+
+}  // namespace
+
+// tile summary: x = sequence-candidate bytes before the tile's first control byte, y = sequence bytes after it,
+// z = headers, w = line type at the tile's end (LT_NONE: no control byte in the tile)
+__global__ void __launch_bounds__(FT_THREADS) fasta_tile_kernel(const uint8_t* __restrict__ text, long long nbytes, int4* __restrict__ tiles) {
+    __shared__ int s_warp[FT_THREADS / 32];
+    __shared__ int s_sum[3];
+    const long long at = (long long)blockIdx.x * FT_TILE + (long long)threadIdx.x * FT_PER;
+    const Bytes16 d = load16(text, nbytes, at);
+    int tile_last;
+    const int before = block_excl_max(last_control(d, threadIdx.x * FT_PER), s_warp, &tile_last);
+    int type = before < 0 ? LT_NONE : (before & 1);
+    int pre = 0, known = 0, nh = 0;
+    uint8_t prev = d.prev;
+#pragma unroll
+    for (int i = 0; i < FT_PER; ++i) {
+        if (i < d.n) {
+            const uint8_t ch = d.b[i];
+            if (ch == '\n') type = LT_SEQ;
+            else if (ch == '>' && prev == '\n') { type = LT_HDR; ++nh; }
+            else if (type == LT_NONE) ++pre;
+            else if (type == LT_SEQ) ++known;
+        }
+        prev = d.b[i];
+    }
+    if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
+    __syncthreads();
+    if (pre) atomicAdd(&s_sum[0], pre);
+    if (known) atomicAdd(&s_sum[1], known);
+    if (nh) atomicAdd(&s_sum[2], nh);
+    __syncthreads();
+    if (threadIdx.x == 0) tiles[blockIdx.x] = make_int4(s_sum[0], s_sum[1], s_sum[2], tile_last < 0 ? LT_NONE : (tile_last & 1));
+}
+
+// One block. info[t] = {sequence bytes before tile t, headers before tile t | line type at its start << 40};
+// totals = {sequence bytes, headers}.
+__global__ void __launch_bounds__(1024) fasta_scan_kernel(const int4* __restrict__ tiles, long long n_tiles, longlong2* __restrict__ info,
+                                                          long long* __restrict__ totals) {
+    __shared__ long long s_a[1024], s_b[1024];
+    __shared__ int s_t[1024];
+    const int t = threadIdx.x;
+    const long long per = (n_tiles + 1023) / 1024, lo = min(n_tiles, t * per), hi = min(n_tiles, lo + per);
+    // line type at the end of this thread's range
+    int type = LT_NONE;
+    for (long long i = lo; i < hi; ++i) { const int w = tiles[i].w; if (w != LT_NONE) type = w; }
+    s_t[t] = type;
+    __syncthreads();
+    int entry = LT_SEQ;  // the text starts in a sequence line (a headerless file is one unnamed record)
+    for (int k = t - 1; k >= 0; --k) if (s_t[k] != LT_NONE) { entry = s_t[k]; break; }
+    long long seq = 0, hdr = 0;
+    type = entry;
+    for (long long i = lo; i < hi; ++i) {
+        const int4 v = tiles[i];
+        seq += (type == LT_SEQ ? v.x : 0) + v.y;
+        hdr += v.z;
+        if (v.w != LT_NONE) type = v.w;
+    }
+    s_a[t] = seq; s_b[t] = hdr;
+    __syncthreads();
+    if (t == 0) {
+        long long a = 0, b = 0;
+        for (int k = 0; k < 1024; ++k) { const long long x = s_a[k], y = s_b[k]; s_a[k] = a; s_b[k] = b; a += x; b += y; }
+        totals[0] = a; totals[1] = b;
+    }
+    __syncthreads();
+    seq = s_a[t]; hdr = s_b[t]; type = entry;
+    for (long long i = lo; i < hi; ++i) {
+        const int4 v = tiles[i];
+        info[i] = make_longlong2(seq, hdr | ((long long)type << 40));
+        seq += (type == LT_SEQ ? v.x : 0) + v.y;
+        hdr += v.z;
+        if (v.w != LT_NONE) type = v.w;
+    }
+}
+
+// bases[] receives the sequence bytes in order; for header k: hdr_pos[k] = offset of its '>' in the text,
+// hdr_seq[k] = number of sequence bytes in front of it (= where the record it names starts in bases[]).
+__global__ void __launch_bounds__(FT_THREADS) fasta_strip_kernel(const uint8_t* __restrict__ text, long long nbytes,
+                                                                 const longlong2* __restrict__ info, uint8_t* __restrict__ bases,
+                                                                 long long* __restrict__ hdr_pos, long long* __restrict__ hdr_seq) {
+    __shared__ int s_warp[FT_THREADS / 32];
+    __shared__ uint8_t s_out[FT_TILE];
+    const long long at = (long long)blockIdx.x * FT_TILE + (long long)threadIdx.x * FT_PER;
+    const Bytes16 d = load16(text, nbytes, at);
+    const longlong2 ti = info[blockIdx.x];
+    const long long seq_base = ti.x, hdr_base = ti.y & ((1ll << 40) - 1);
+    const int entry = (int)(ti.y >> 40);
+    const int before = block_excl_max(last_control(d, threadIdx.x * FT_PER), s_warp, nullptr);
+    const int type0 = before < 0 ? entry : (before & 1);
+    int type = type0, ns = 0, nh = 0;
+    uint8_t prev = d.prev;
+#pragma unroll
+    for (int i = 0; i < FT_PER; ++i) {
+        if (i < d.n) {
+            const uint8_t ch = d.b[i];
+            if (ch == '\n') type = LT_SEQ;
+            else if (ch == '>' && prev == '\n') { type = LT_HDR; ++nh; }
+            else if (type == LT_SEQ) ++ns;
+        }
+        prev = d.b[i];
+    }
+    int tile_seq;
+    const int rank = block_excl_sum(ns, s_warp, &tile_seq);
+    const int hrank = block_excl_sum(nh, s_warp, nullptr);
+    type = type0; prev = d.prev;
+    int r = rank, h = hrank;
+#pragma unroll
+    for (int i = 0; i < FT_PER; ++i) {
+        if (i < d.n) {
+            const uint8_t ch = d.b[i];
+            if (ch == '\n') type = LT_SEQ;
+            else if (ch == '>' && prev == '\n') {
+                type = LT_HDR;
+                hdr_pos[hdr_base + h] = at + i;
+                hdr_seq[hdr_base + h] = seq_base + r;
+                ++h;
+            } else if (type == LT_SEQ) s_out[r++] = ch;
+        }
+        prev = d.b[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tile_seq; i += FT_THREADS) bases[seq_base + i] = s_out[i];
+}
+
+long long fasta_tiles(long long nbytes) { return (nbytes + FT_TILE - 1) / FT_TILE; }
+
+void launch_fasta_count(const void* text, long long nbytes, void* tiles, void* info, long long* totals, cudaStream_t st) {
+    const long long nt = fasta_tiles(nbytes);
+    if (nt > 0) fasta_tile_kernel<<<(unsigned)nt, FT_THREADS, 0, st>>>((const uint8_t*)text, nbytes, (int4*)tiles);
+    fasta_scan_kernel<<<1, 1024, 0, st>>>((const int4*)tiles, nt, (longlong2*)info, totals);
+}
+
+void launch_fasta_strip(const void* text, long long nbytes, const void* info, void* bases, long long* hdr_pos, long long* hdr_seq,
+                        cudaStream_t st) {
+    const long long nt = fasta_tiles(nbytes);
+    if (nt > 0)
+        fasta_strip_kernel<<<(unsigned)nt, FT_THREADS, 0, st>>>((const uint8_t*)text, nbytes, (const longlong2*)info, (uint8_t*)bases,
+                                                                hdr_pos, hdr_seq);
+}
+
+}  // namespace rb

@@ -61,6 +61,12 @@ void launch_seed_filter(const DevBatch& b, const void* seeds, long long n, void*
 // caller; afterwards keys[i] = count << 32 | (0x7FFFFFFF - row) of the seed's best row, 0 if no row scores
 static const int MOTIF_SLAB = 256;
 void launch_motif_rows(const DevBatch& b, const void* seeds, const void* items, long long n_items, void* keys, cudaStream_t st);
+// K0 (fasta_kernels.cu): FASTA text on the device -> sequence bytes + header table. tiles: int4[fasta_tiles], info:
+// longlong2[fasta_tiles], totals: {sequence bytes, headers} (device)
+long long fasta_tiles(long long nbytes);
+void launch_fasta_count(const void* text, long long nbytes, void* tiles, void* info, long long* totals, cudaStream_t st);
+void launch_fasta_strip(const void* text, long long nbytes, const void* info, void* bases, long long* hdr_pos, long long* hdr_seq,
+                        cudaStream_t st);
 // anchor planes A_s, s = s_lo .. s_lo+ns-1, of one contig: out[(s - s_lo) * nw + w]
 void launch_anchor_planes(const PlaneWord* cw, int L, int nw, int s_lo, int ns, uint32_t* out, cudaStream_t st);
 // LOP3 + SHF warp-lane operations per second the device sustains (integer-pipe roofline denominator)

@@ -22,7 +22,10 @@ STREAM_NAMES = ("perfect", "subst", "anchored")
 
 EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
            "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes",
-           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact", "rb_motif_rows")
+           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact", "rb_motif_rows", "rb_load_fasta", "rb_fasta_records")
+
+
+FASTA_REC_DTYPE = np.dtype([("name_off", "<i8"), ("name_len", "<i4"), ("length", "<i4")])
 
 
 class RbParams(ctypes.Structure):
@@ -95,6 +98,10 @@ def load_library(path=LIB_PATH):
     lib.rb_get_timing.argtypes = [ctypes.c_void_p, ctypes.POINTER(RbTiming)]
     lib.rb_filter_seeds.restype = ctypes.c_int
     lib.rb_filter_seeds.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.rb_load_fasta.restype = ctypes.c_int
+    lib.rb_load_fasta.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
+    lib.rb_fasta_records.restype = ctypes.c_int
+    lib.rb_fasta_records.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
     lib.rb_motif_rows.restype = ctypes.c_int
     lib.rb_motif_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.rb_measure_int_peak.restype = ctypes.c_int
@@ -168,6 +175,20 @@ class Scanner:
                                                     len(lengths)))
         self.n_contigs = len(lengths)
         self.lengths = lengths
+
+    def load_fasta(self, text):
+        """text: FASTA file content (bytes or uint8 array). Parsed on the device (rb_load_fasta, the reference's reader
+        quirks of ribbit.cpp:269-280); the records become the loaded contigs. Returns (names, lengths)."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
+        n = ctypes.c_int32(0)
+        self._check(self.lib.rb_load_fasta(self.ctx, buf.ctypes.data if buf.size else None, buf.size, ctypes.byref(n)))
+        rec = np.zeros(n.value, dtype=FASTA_REC_DTYPE)
+        self._check(self.lib.rb_fasta_records(self.ctx, rec.ctypes.data, n.value))
+        names = ["" if o < 0 else bytes(buf[o:o + l]).decode(errors="replace") for o, l in zip(rec["name_off"], rec["name_len"])]
+        self.n_contigs = n.value
+        self.lengths = rec["length"].astype(np.int32)
+        self._keep = None
+        return names, self.lengths.copy()
 
     def scan_device(self):
         self._check(self.lib.rb_scan_device(self.ctx))
