@@ -287,6 +287,41 @@ def run_gpu(args):
         sc2.scan(copy=False)
     e2e_serial = L * args.steps / (time.perf_counter() - t0) / 1e9
 
+    # ---- the rows next to the path that are built, measured outside the timed regions, rank 0 only:
+    # K0 rb_load_fasta (80-column FASTA text of the same contig, pinned host memory -> contigs on the device) and
+    # K7 rb_motif_rows (seeds = the scan's own kept anchored candidates with motif sizes > 10, N-truncated by K5)
+    next_rows = None
+    if rank == 0:
+        body = np.frombuffer(contig, dtype=np.uint8)
+        full = (L // 80) * 80
+        lines = np.concatenate([body[:full].reshape(-1, 80), np.full((full // 80, 1), 10, np.uint8)], axis=1).reshape(-1)
+        text_np = np.concatenate([np.frombuffer(b">chr21 synthetic\n", np.uint8), lines, body[full:], np.frombuffer(b"\n", np.uint8)])
+        text = torch.empty(len(text_np), dtype=torch.uint8).pin_memory()
+        text.numpy()[:] = text_np
+        t_fa = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            names, lens = sc2.load_fasta(text.numpy())
+            t_fa.append(time.perf_counter() - t0)
+        assert names == ["chr21"] and lens.tolist() == [L]
+        sc2.scan_device()
+        assert sc2.counts() == counts, "streams differ after rb_load_fasta"
+        a = sc2.fetch(copy=False)[2][0]
+        a = a[(a["mlen"] > 10) & (a["flags"] == 0)][:400_000]
+        seeds = np.stack([np.zeros(len(a), np.int32), a["start"], a["end"], a["mlen"].astype(np.int32)], axis=1).astype(np.int32)
+        info = sc2.filter_seeds(seeds)
+        seeds[:, 2] = np.minimum(seeds[:, 1] + info[:, 0], L)
+        t_mr = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rows = sc2.motif_rows(seeds)
+            t_mr.append(time.perf_counter() - t0)
+        next_rows = {"k0_load_fasta": {"text_bytes": int(len(text_np)), "ms": min(t_fa[1:]) * 1e3, "gbp_per_s": L / min(t_fa[1:]) / 1e9,
+                                       "what": "rb_load_fasta from pinned host memory: H2D of the text + 3 kernels + header table D2H"},
+                     "k7_motif_rows": {"seeds": int(len(seeds)), "ms": min(t_mr) * 1e3, "seeds_per_s": len(seeds) / min(t_mr),
+                                       "scored": int((rows[:, 1] > 0).sum()),
+                                       "what": "rb_motif_rows on the scan's kept anchored candidates with mlen > 10 (whole call: H2D of the seeds, kernel, D2H)"}}
+
     if rank == 0:
         scan_ms_avg = float(np.mean(scan_ms))
         ops_per_launch = OPS_PER_BASE * L                   # lane-operations (one 32-bit op in one lane = 32 bases x 1 op)
@@ -327,6 +362,7 @@ def run_gpu(args):
                          "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "peak_source": "measured" if peaks else "fallback"}},
             "cpu_baseline": {"value": cpu_v, "unit": "Gbp/s", "cores": cpu_cores, "kind": cpu_kind, "sample": cpu_what},
+            "next_rows": next_rows,
         }
         print(json.dumps(line), flush=True)
     sc.close(); sc2.close(); pipe.close()
