@@ -21,26 +21,64 @@ constexpr int FT_TILE = FT_THREADS * FT_PER;  // 4096 bytes
 
 enum : int { LT_SEQ = 0, LT_HDR = 1, LT_NONE = 2 };
 
-struct Bytes16 {
-    uint8_t b[FT_PER];
-    uint8_t prev;  // byte in front of b[0] ('\n' in front of the text)
-    int n;         // valid bytes
+// 16 bytes of text as bit masks (bit i = byte i of the thread's slice): newlines, header starts ('>' behind a '\n'),
+// header bytes that follow a header start inside the slice, and the bytes in front of the slice's first control byte
+// (their line type comes from earlier slices). Byte-parallel: __vcmpeq4 + one multiply per word gathers the four
+// compare results into a nibble.
+struct Slice {
+    uint32_t w[4];     // the bytes
+    uint32_t valid;    // bytes inside the text
+    uint32_t nl, hs;   // control bytes
+    uint32_t hdr;      // bytes of header lines that start inside the slice (the '>' included, the '\n' not)
+    uint32_t before;   // valid bytes in front of the first control byte
 };
 
-__device__ __forceinline__ Bytes16 load16(const uint8_t* __restrict__ text, long long nbytes, long long at) {
-    Bytes16 r;
-    r.n = (int)max(0ll, min((long long)FT_PER, nbytes - at));
-    if (r.n == FT_PER && ((reinterpret_cast<uintptr_t>(text + at) & 15) == 0)) {
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t word, uint32_t pattern) {
+    return ((__vcmpeq4(word, pattern) & 0x08040201u) * 0x01010101u) >> 24;  // bit k = byte k equals
+}
+
+__device__ __forceinline__ Slice load_slice(const uint8_t* __restrict__ text, long long nbytes, long long at) {
+    Slice r;
+    const int n = (int)max(0ll, min((long long)FT_PER, nbytes - at));
+    if (n == FT_PER) {  // text comes from cudaMalloc and `at` is a multiple of 16
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + at));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < FT_PER; ++i) r.b[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < FT_PER; ++i) r.b[i] = (i < r.n) ? __ldg(text + at + i) : (uint8_t)'\n';
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * k + j < n) x |= (uint32_t)__ldg(text + at + 4 * k + j) << (8 * j);
+            r.w[k] = x;
+        }
     }
-    r.prev = (at > 0 && at <= nbytes) ? __ldg(text + at - 1) : (uint8_t)'\n';
+    r.valid = (1u << n) - 1u;
+    uint32_t nl = 0, gt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        nl |= eq_mask4(r.w[k], 0x0A0A0A0Au) << (4 * k);
+        gt |= eq_mask4(r.w[k], 0x3E3E3E3Eu) << (4 * k);
+    }
+    const uint32_t prev_nl = (at > 0 && at <= nbytes) ? (__ldg(text + at - 1) == '\n') : 1u;  // the text starts a line
+    r.nl = nl & r.valid;
+    r.hs = gt & ((r.nl << 1) | prev_nl) & r.valid;
+    // a header start at bit a and its newline at bit b > a: (X - hs) ^ X covers a..b (no other control byte lies between)
+    const uint32_t X = r.nl | 0x10000u;
+    r.hdr = ((X - r.hs) ^ X) & ~r.nl & 0xFFFFu;
+    const uint32_t ctrl = r.nl | r.hs;
+    r.before = (ctrl ? ((ctrl & (0u - ctrl)) - 1u) : 0xFFFFu) & r.valid;
     return r;
+}
+
+__device__ __forceinline__ uint32_t slice_byte(const Slice& d, int i) { return (d.w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
+
+// The slice's last control byte as (index in tile) * 2 + line type it starts, -1 if none.
+__device__ __forceinline__ int last_control(const Slice& d, int first_index) {
+    const uint32_t ctrl = d.nl | d.hs;
+    if (!ctrl) return -1;
+    const int pos = 31 - __clz((int)ctrl);
+    return (first_index + pos) * 2 + (int)((d.hs >> pos) & 1u);
 }
 
 // inclusive max-scan over the block (values >= -1); returns the EXCLUSIVE result for this thread, *total = block max
@@ -91,21 +129,6 @@ __device__ __forceinline__ int block_excl_sum(int v, int* s_warp, int* total) {
     return before + x - v;
 }
 
-// The thread's last control byte as (index in tile) * 2 + line type it starts, -1 if none.
-__device__ __forceinline__ int last_control(const Bytes16& d, int first_index) {
-    int last = -1;
-    uint8_t prev = d.prev;
-#pragma unroll
-    for (int i = 0; i < FT_PER; ++i) {
-        if (i < d.n) {
-            if (d.b[i] == '\n') last = (first_index + i) * 2 + LT_SEQ;
-            else if (d.b[i] == '>' && prev == '\n') last = (first_index + i) * 2 + LT_HDR;
-        }
-        prev = d.b[i];
-    }
-    return last;
-}
-
 }  // namespace
 
 // tile summary: x = sequence-candidate bytes before the tile's first control byte, y = sequence bytes after it,
@@ -114,28 +137,23 @@ __global__ void __launch_bounds__(FT_THREADS) fasta_tile_kernel(const uint8_t* _
     __shared__ int s_warp[FT_THREADS / 32];
     __shared__ int s_sum[3];
     const long long at = (long long)blockIdx.x * FT_TILE + (long long)threadIdx.x * FT_PER;
-    const Bytes16 d = load16(text, nbytes, at);
+    const Slice d = load_slice(text, nbytes, at);
+    if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
     int tile_last;
     const int before = block_excl_max(last_control(d, threadIdx.x * FT_PER), s_warp, &tile_last);
-    int type = before < 0 ? LT_NONE : (before & 1);
-    int pre = 0, known = 0, nh = 0;
-    uint8_t prev = d.prev;
-#pragma unroll
-    for (int i = 0; i < FT_PER; ++i) {
-        if (i < d.n) {
-            const uint8_t ch = d.b[i];
-            if (ch == '\n') type = LT_SEQ;
-            else if (ch == '>' && prev == '\n') { type = LT_HDR; ++nh; }
-            else if (type == LT_NONE) ++pre;
-            else if (type == LT_SEQ) ++known;
-        }
-        prev = d.b[i];
+    const int type = before < 0 ? LT_NONE : (before & 1);
+    const int n_before = __popc(d.before), n_after = __popc(d.valid & ~d.before & ~d.nl & ~d.hdr);
+    int pre = type == LT_NONE ? n_before : 0;
+    int known = n_after + (type == LT_SEQ ? n_before : 0);
+    int nh = __popc(d.hs);
+    pre = __reduce_add_sync(0xFFFFFFFFu, pre);
+    known = __reduce_add_sync(0xFFFFFFFFu, known);
+    nh = __reduce_add_sync(0xFFFFFFFFu, nh);
+    if ((threadIdx.x & 31) == 0) {
+        if (pre) atomicAdd(&s_sum[0], pre);
+        if (known) atomicAdd(&s_sum[1], known);
+        if (nh) atomicAdd(&s_sum[2], nh);
     }
-    if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
-    __syncthreads();
-    if (pre) atomicAdd(&s_sum[0], pre);
-    if (known) atomicAdd(&s_sum[1], known);
-    if (nh) atomicAdd(&s_sum[2], nh);
     __syncthreads();
     if (threadIdx.x == 0) tiles[blockIdx.x] = make_int4(s_sum[0], s_sum[1], s_sum[2], tile_last < 0 ? LT_NONE : (tile_last & 1));
 }
@@ -189,42 +207,30 @@ __global__ void __launch_bounds__(FT_THREADS) fasta_strip_kernel(const uint8_t* 
     __shared__ int s_warp[FT_THREADS / 32];
     __shared__ uint8_t s_out[FT_TILE];
     const long long at = (long long)blockIdx.x * FT_TILE + (long long)threadIdx.x * FT_PER;
-    const Bytes16 d = load16(text, nbytes, at);
+    const Slice d = load_slice(text, nbytes, at);
     const longlong2 ti = info[blockIdx.x];
     const long long seq_base = ti.x, hdr_base = ti.y & ((1ll << 40) - 1);
     const int entry = (int)(ti.y >> 40);
     const int before = block_excl_max(last_control(d, threadIdx.x * FT_PER), s_warp, nullptr);
     const int type0 = before < 0 ? entry : (before & 1);
-    int type = type0, ns = 0, nh = 0;
-    uint8_t prev = d.prev;
-#pragma unroll
-    for (int i = 0; i < FT_PER; ++i) {
-        if (i < d.n) {
-            const uint8_t ch = d.b[i];
-            if (ch == '\n') type = LT_SEQ;
-            else if (ch == '>' && prev == '\n') { type = LT_HDR; ++nh; }
-            else if (type == LT_SEQ) ++ns;
-        }
-        prev = d.b[i];
-    }
+    const uint32_t seq = (d.valid & ~d.before & ~d.nl & ~d.hdr) | (type0 == LT_SEQ ? d.before : 0u);
     int tile_seq;
-    const int rank = block_excl_sum(ns, s_warp, &tile_seq);
-    const int hrank = block_excl_sum(nh, s_warp, nullptr);
-    type = type0; prev = d.prev;
-    int r = rank, h = hrank;
+    const int rank = block_excl_sum(__popc(seq), s_warp, &tile_seq);
+    const int hrank = block_excl_sum(__popc(d.hs), s_warp, nullptr);
+    if (seq == 0xFFFFu) {
 #pragma unroll
-    for (int i = 0; i < FT_PER; ++i) {
-        if (i < d.n) {
-            const uint8_t ch = d.b[i];
-            if (ch == '\n') type = LT_SEQ;
-            else if (ch == '>' && prev == '\n') {
-                type = LT_HDR;
-                hdr_pos[hdr_base + h] = at + i;
-                hdr_seq[hdr_base + h] = seq_base + r;
-                ++h;
-            } else if (type == LT_SEQ) s_out[r++] = ch;
-        }
-        prev = d.b[i];
+        for (int i = 0; i < FT_PER; ++i) s_out[rank + i] = (uint8_t)slice_byte(d, i);
+    } else {
+        int r = rank;
+#pragma unroll
+        for (int i = 0; i < FT_PER; ++i)
+            if ((seq >> i) & 1u) s_out[r++] = (uint8_t)slice_byte(d, i);
+    }
+    for (uint32_t h = d.hs; h; h &= h - 1u) {
+        const int i = __ffs((int)h) - 1;
+        const long long k = hdr_base + hrank + __popc(d.hs & ((1u << i) - 1u));
+        hdr_pos[k] = at + i;
+        hdr_seq[k] = seq_base + rank + __popc(seq & ((1u << i) - 1u));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < tile_seq; i += FT_THREADS) bases[seq_base + i] = s_out[i];

@@ -3,7 +3,7 @@
 import re, subprocess, sys, tempfile, os, collections
 lib, kern = sys.argv[1], sys.argv[2]
 td = tempfile.mkdtemp()
-subprocess.run("cd %s && cuobjdump -xelf all %s > /dev/null && nvdisasm -c kernels.sm_100a.cubin > dis.txt" % (td, os.path.abspath(lib)), shell=True, check=True)
+subprocess.run("cd %s && cuobjdump -xelf all %s > /dev/null && for f in *.cubin; do nvdisasm -c $f; done > dis.txt" % (td, os.path.abspath(lib)), shell=True, check=True)
 lines = open(os.path.join(td, "dis.txt")).read().split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and kern in l and l.endswith(":"))
 body = []
