@@ -116,7 +116,10 @@ struct GpuSink {
 static const int SCAN_WARPS = 1;
 
 template <int BW>
-__global__ void __launch_bounds__(SCAN_WARPS * 32, 20) scan_kernel(DevBatch b) {
+#ifndef RB_SCAN_BLOCKS_PER_SM
+#define RB_SCAN_BLOCKS_PER_SM 20
+#endif
+__global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_kernel(DevBatch b) {
     constexpr int GROUPS = 32 / BW;
     __shared__ int s_cnt[SCAN_WARPS][GROUPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
