@@ -128,6 +128,18 @@ typedef struct rb_fasta_record {
 int rb_load_fasta(rb_ctx *ctx, const char *text, int64_t nbytes, int32_t *n_records);
 int rb_fasta_records(rb_ctx *ctx, rb_fasta_record *out, int32_t capacity);
 
+/* One contig over several GPUs (unit = (contig, chunk)). After loading a batch of exactly ONE contig,
+ * rb_set_word_range restricts the following scans to the 32-base words [word_first, word_last) of it (word_last = -1:
+ * to the end; the part that ends at the last word also owns the tail flush). The streams then hold exactly the
+ * candidates whose emission time falls into those words, in order, so the parts of a partition of the contig
+ * concatenate to the full streams — with one fix-up: a PSEUDO record carries the largest end of the candidates elided
+ * since the contig start, and a part only knows its own. rb_get_elided_max returns, for the substitution and the
+ * anchored stream, the largest elided end of the scanned part (-1: none); the host raises every PSEUDO end of a later
+ * part to the maximum over the earlier parts (ribbit_b200/shard.py: stitch_parts). Every part needs the whole contig
+ * loaded: warm-up and N-run handling read the words in front of the range. */
+int rb_set_word_range(rb_ctx *ctx, int32_t word_first, int32_t word_last);
+int rb_get_elided_max(rb_ctx *ctx, int64_t out[2]);
+
 /* Runs pack + scan + ordered compaction on the device; results stay in device memory. */
 int rb_scan_device(rb_ctx *ctx);
 

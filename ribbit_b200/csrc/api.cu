@@ -45,6 +45,7 @@ struct rb_ctx {
     long long dst_cap = 0;
     bool loaded = false, scanned = false;
     bool ascii_external = false;
+    bool ranged = false;  // rb_set_word_range: only part of the (single) contig is scanned
     const void* ascii_dev_ext = nullptr;
 
     DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
@@ -123,6 +124,24 @@ int records_per_word(const BandLayout& lay, int band) {
     return m0 <= 12 ? 12 : 6;
 }
 
+// Cuts the contigs' words into chunks. range_last >= 0: single-contig batch, only words [range_first, range_last).
+void make_chunks(rb_ctx* c, long long total_words, int range_first, int range_last) {
+    const BandLayout& lay = c->lay;
+    int cw = c->params.chunk_words;
+    if (cw <= 0) {
+        const long long target_chunks = std::max<long long>(1, 148ll * 64 / lay.nbands);
+        cw = (int)std::min<long long>(1 << 20, std::max<long long>(64, (total_words + target_chunks - 1) / target_chunks));
+    }
+    c->chunks.clear();
+    const int n = (int)c->contigs.size();
+    for (int i = 0; i < n; ++i) {
+        const int nw = c->contigs[i].nw;
+        if (nw == 0) { c->chunks.push_back(Chunk{i, 0, 0, 1}); continue; }
+        const int lo = range_last >= 0 ? range_first : 0, hi = range_last >= 0 ? range_last : nw;
+        for (int w = lo; w < hi; w += cw) c->chunks.push_back(Chunk{i, w, std::min(hi, w + cw), std::min(hi, w + cw) >= nw ? 1 : 0});
+    }
+}
+
 int build_geometry(rb_ctx* c, const int64_t* offsets, const int32_t* lengths, int32_t n) {
     const BandLayout& lay = c->lay;
     c->contigs.resize(n);
@@ -146,17 +165,8 @@ int build_geometry(rb_ctx* c, const int64_t* offsets, const int32_t* lengths, in
     c->plane_start[n] = pw;
     c->bucket_base[n] = nb;
 
-    int cw = c->params.chunk_words;
-    if (cw <= 0) {
-        const long long target_chunks = std::max<long long>(1, 148ll * 64 / lay.nbands);
-        cw = (int)std::min<long long>(1 << 20, std::max<long long>(64, (total_words + target_chunks - 1) / target_chunks));
-    }
-    c->chunks.clear();
-    for (int i = 0; i < n; ++i) {
-        const int nw = c->contigs[i].nw;
-        if (nw == 0) { c->chunks.push_back(Chunk{i, 0, 0, 1}); continue; }
-        for (int w = 0; w < nw; w += cw) c->chunks.push_back(Chunk{i, w, std::min(nw, w + cw), w + cw >= nw ? 1 : 0});
-    }
+    c->ranged = false;
+    make_chunks(c, total_words, 0, -1);
     return RB_OK;
 }
 
@@ -392,6 +402,43 @@ int rb_fasta_records(rb_ctx* c, rb_fasta_record* out, int32_t capacity) {
     return RB_OK;
 }
 
+int rb_set_word_range(rb_ctx* c, int32_t word_first, int32_t word_last) {
+    if (!c) return RB_E_ARG;
+    if (!c->loaded) return fail(c, RB_E_STATE, "rb_set_word_range: no contigs loaded");
+    if (c->contigs.size() != 1) return fail(c, RB_E_STATE, "rb_set_word_range: needs a batch of exactly one contig");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    const int nw = c->contigs[0].nw;
+    if (word_last < 0) word_last = nw;
+    if (word_first < 0 || word_first > word_last || word_last > nw || (nw > 0 && word_first == word_last))
+        return fail(c, RB_E_ARG, "rb_set_word_range: [%d, %d) is not a non-empty range of the contig's %d words", word_first, word_last, nw);
+    c->ranged = !(word_first == 0 && word_last == nw);
+    make_chunks(c, std::max(1, word_last - word_first), word_first, word_last);
+    size_items(c, nullptr);
+    int rc;
+    if ((rc = upload(c, c->d_chunks, c->chunks))) return rc;
+    c->batch.chunks = (const Chunk*)c->d_chunks.p;
+    c->batch.n_chunks = (int)c->chunks.size();
+    c->batch.n_items = (long long)c->chunks.size() * c->lay.nbands;
+    if ((rc = upload_items(c))) return rc;
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->scanned = false;
+    return RB_OK;
+}
+
+int rb_get_elided_max(rb_ctx* c, int64_t out[2]) {
+    if (!c || !out) return RB_E_ARG;
+    if (!c->scanned) return fail(c, RB_E_STATE, "rb_get_elided_max: no scan result");
+    if (c->contigs.size() != 1) return fail(c, RB_E_STATE, "rb_get_elided_max: needs a batch of exactly one contig");
+    RB_CUDA(c, cudaSetDevice(c->device));
+    BlockPartial tot{};
+    if (c->batch.n_buckets > 0) {
+        RB_CUDA(c, cudaMemcpyAsync(&tot, c->batch.partial + c->batch.n_merge_blocks, sizeof tot, cudaMemcpyDeviceToHost, c->stream));
+        RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    for (int s = 0; s < 2; ++s) out[s] = tot.emax[s] ? (int64_t)(tot.emax[s] & 0xFFFFFFFFull) - 1 : -1;
+    return RB_OK;
+}
+
 int rb_scan_device(rb_ctx* c) {
     if (!c) return RB_E_ARG;
     if (!c->loaded) return fail(c, RB_E_STATE, "rb_scan_device: no contigs loaded");
@@ -405,6 +452,8 @@ int rb_scan_device(rb_ctx* c) {
     RB_CUDA(c, cudaEventRecord(c->ev[1], st));
     for (int attempt = 0;; ++attempt) {
         RB_CUDA(c, cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), st));
+        if (c->ranged)  // buckets outside the range are written by no chunk: they must read as empty
+            RB_CUDA(c, cudaMemsetAsync(b.meta, 0, (size_t)b.n_buckets * c->lay.nbands * sizeof(Meta), st));
         launch_scan(b, st);
         tm.launches += b.n_items ? 1 : 0;
         if (attempt == 0) RB_CUDA(c, cudaEventRecord(c->ev[2], st));

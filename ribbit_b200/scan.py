@@ -22,7 +22,7 @@ STREAM_NAMES = ("perfect", "subst", "anchored")
 
 EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
            "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes",
-           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact", "rb_motif_rows", "rb_load_fasta", "rb_fasta_records")
+           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact", "rb_motif_rows", "rb_load_fasta", "rb_fasta_records", "rb_set_word_range", "rb_get_elided_max")
 
 
 FASTA_REC_DTYPE = np.dtype([("name_off", "<i8"), ("name_len", "<i4"), ("length", "<i4")])
@@ -102,6 +102,10 @@ def load_library(path=LIB_PATH):
     lib.rb_load_fasta.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
     lib.rb_fasta_records.restype = ctypes.c_int
     lib.rb_fasta_records.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+    lib.rb_set_word_range.restype = ctypes.c_int
+    lib.rb_set_word_range.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
+    lib.rb_get_elided_max.restype = ctypes.c_int
+    lib.rb_get_elided_max.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
     lib.rb_motif_rows.restype = ctypes.c_int
     lib.rb_motif_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.rb_measure_int_peak.restype = ctypes.c_int
@@ -189,6 +193,16 @@ class Scanner:
         self.lengths = rec["length"].astype(np.int32)
         self._keep = None
         return names, self.lengths.copy()
+
+    def set_word_range(self, word_first, word_last=-1):
+        """Single-contig batch: scan only the 32-base words [word_first, word_last) (rb_set_word_range)."""
+        self._check(self.lib.rb_set_word_range(self.ctx, word_first, word_last))
+
+    def elided_max(self):
+        """Largest end of the candidates elided in the scanned part, per stream (subst, anchored); -1 = none."""
+        out = (ctypes.c_int64 * 2)()
+        self._check(self.lib.rb_get_elided_max(self.ctx, out))
+        return [int(out[0]), int(out[1])]
 
     def scan_device(self):
         self._check(self.lib.rb_scan_device(self.ctx))

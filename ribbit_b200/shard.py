@@ -2,6 +2,10 @@
 scans its own contigs and the per-contig streams are reassembled in input order. No collective is on the data path;
 torch.distributed is used only to collect the results (gather_object) — or not at all when every rank writes its own
 output.
+
+One contig over several GPUs (scan_contig_split): every rank loads the contig, scans its own range of 32-base words
+(rb_set_word_range) and the parts are concatenated in rank order; the only fix-up is the end carried by PSEUDO records
+(stitch_parts).
 """
 from typing import Callable, Dict, List, Sequence
 
@@ -55,5 +59,70 @@ def gpu_scan_fn(min_mlen=2, max_mlen=100, device=0):
         sc.load(batch)
         res = sc.scan()
         return [scan.contig_streams(res, i) for i in range(len(batch))]
+
+    return fn
+
+
+PSEUDO = 2  # rb_rec flag (include/ribbit_scan.h)
+
+
+def split_words(n_words: int, parts: int) -> List[tuple]:
+    """[first, last) word ranges of a contig of n_words words for `parts` ranks: equal shares, empty ranges dropped
+    (a contig shorter than `parts` words keeps fewer parts)."""
+    parts = max(1, min(parts, max(n_words, 1)))
+    cuts = [n_words * k // parts for k in range(parts + 1)]
+    return [(cuts[k], cuts[k + 1]) for k in range(parts) if cuts[k + 1] > cuts[k] or n_words == 0]
+
+
+def stitch_parts(parts: Sequence[dict], elided: Sequence[Sequence[int]]) -> dict:
+    """parts[r] = {1|2|3: rows (start, end, mlen, flags, time)} of word range r (in contig order), elided[r] = the largest
+    end among the candidates elided in part r for the substitution and the anchored stream (-1: none). Returns the streams
+    of the whole contig: the parts back to back, the end of every PSEUDO record raised to the largest elided end of the
+    earlier parts (a PSEUDO record carries the largest end elided since the contig start, and a part only saw its own)."""
+    import numpy as np
+    out = {}
+    for s in (1, 2, 3):
+        rows = [np.array(p[s], copy=True) for p in parts]
+        if s != 1:
+            carry = -1
+            for r, a in enumerate(rows):
+                if r > 0 and carry >= 0 and len(a):
+                    ps = (a[:, 3] & PSEUDO) != 0
+                    a[ps, 1] = np.maximum(a[ps, 1], carry)
+                carry = max(carry, int(elided[r][s - 2]))
+        out[s] = np.concatenate(rows) if rows else np.zeros((0, 5), dtype=np.int64)
+    return out
+
+
+def scan_contig_split(contig: bytes, part_fn: Callable[[bytes, int, int], tuple], rank: int = 0, world: int = 1, gather: bool = True):
+    """One contig over `world` ranks. part_fn(contig, word_first, word_last) -> (streams, [elided_S, elided_A]) scans one
+    word range. With gather=True rank 0 returns the stitched streams of the whole contig (other ranks None)."""
+    ranges = split_words((len(contig) + 31) // 32, world)
+    local = part_fn(contig, *ranges[rank]) if rank < len(ranges) else None
+    if not gather:
+        return local
+    if world == 1:
+        gathered = [local]
+    else:
+        import torch.distributed as dist
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(local, gathered, dst=0)
+        if rank != 0:
+            return None
+    got = [g for g in gathered if g is not None]
+    return stitch_parts([g[0] for g in got], [g[1] for g in got])
+
+
+def gpu_part_fn(min_mlen=2, max_mlen=100, device=0):
+    """part_fn backed by the CUDA library: the whole contig is loaded (warm-up and N-run handling read the words in
+    front of the range), only the words of the range are scanned."""
+    from . import scan
+    sc = scan.Scanner(min_mlen, max_mlen, device=device)
+
+    def fn(contig, word_first, word_last):
+        sc.load([contig])
+        sc.set_word_range(word_first, word_last)
+        res = sc.scan()
+        return scan.contig_streams(res, 0), sc.elided_max()
 
     return fn

@@ -50,13 +50,14 @@ def fast_words(seq: bytes):
     return fast
 
 
-def expected_streams(seq: bytes, events: np.ndarray):
+def expected_streams(seq: bytes, events: np.ndarray, with_elided: bool = False):
     """events: oracle rows (stream 1..3, start, end, mlen, time). Returns dict stream->(n,5) rows
-    (start, end, mlen, flags, time)."""
+    (start, end, mlen, flags, time); with_elided: also [largest elided end of stream 2, of stream 3] (-1: none)."""
     L = len(seq)
     nw = (L + 31) // 32
     fast = fast_words(seq)
     out = {}
+    elided_max = []
     for stream in (1, 2, 3):
         ev = events[events[:, 0] == stream]
         rows = []
@@ -102,4 +103,6 @@ def expected_streams(seq: bytes, events: np.ndarray):
             cur_bucket = bucket
             rows.append((s, e, m, flags, 32 * nw if is_tail else t))
         out[stream] = np.array(rows, dtype=np.int64).reshape(-1, 5)
-    return out
+        if stream != 1:
+            elided_max.append(last_elided_time - 8 if last_elided_time >= 0 else -1)
+    return (out, elided_max) if with_elided else out

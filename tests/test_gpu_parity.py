@@ -321,3 +321,38 @@ def test_compact_fetch_equals_full_fetch(built):
         nlong += len(lg)
     assert nlong > 0
     sc.close()
+
+
+@pytest.mark.gpu
+def test_contig_split_over_word_ranges():
+    """SURVEY.md §8e, unit = (contig, chunk): one contig scanned as 2..9 word ranges (rb_set_word_range), stitched by
+    shard.stitch_parts, equals the unsplit scan — boundaries fall inside N runs and repeats."""
+    from ribbit_b200 import shard
+    rng = np.random.default_rng(31)
+    seq = bytearray(synth.contig_c2(300_000, seed=8, density_per_mbp=1500))
+    seq[100_000:100_900] = b"N" * 900
+    seq[150_016:150_016 + 37 * 60] = bytes(rng.choice(list(b"ACGT"), 37).astype(np.uint8)) * 60   # a repeat across the 2-way cut
+    seq = bytes(seq)
+    for lo, hi in ((2, 100), (1, 6)):
+        sc = scan.Scanner(lo, hi)
+        sc.load([seq])
+        whole = scan.contig_streams(sc.scan(), 0)
+        part_fn = shard.gpu_part_fn(lo, hi)
+        nw = (len(seq) + 31) // 32
+        for world in (2, 3, 9):
+            parts = [part_fn(seq, a, b) for a, b in shard.split_words(nw, world)]
+            got = shard.stitch_parts([p[0] for p in parts], [p[1] for p in parts])
+            for s in (1, 2, 3):
+                assert np.array_equal(got[s], whole[s]), (lo, hi, world, s)
+        assert sum(len(p[0][3]) for p in parts) == len(whole[3])
+        # a range set and then cleared gives the whole contig again; argument checks
+        sc.load([seq]); sc.set_word_range(10, 20); sc.set_word_range(0, -1)
+        again = scan.contig_streams(sc.scan(), 0)
+        for s in (1, 2, 3):
+            assert np.array_equal(again[s], whole[s])
+        for bad in ((5, 5), (-1, 4), (3, nw + 1), (9, 2)):
+            with pytest.raises(scan.RibbitScanError):
+                sc.set_word_range(*bad)
+        sc.load([seq, seq[:100]])
+        with pytest.raises(scan.RibbitScanError):
+            sc.set_word_range(0, 1)
