@@ -45,7 +45,6 @@ struct rb_ctx {
     long long dst_cap = 0;
     bool loaded = false, scanned = false;
     bool ascii_external = false;
-    bool ranged = false;  // rb_set_word_range: only part of the (single) contig is scanned
     const void* ascii_dev_ext = nullptr;
 
     DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
@@ -165,7 +164,6 @@ int build_geometry(rb_ctx* c, const int64_t* offsets, const int32_t* lengths, in
     c->plane_start[n] = pw;
     c->bucket_base[n] = nb;
 
-    c->ranged = false;
     make_chunks(c, total_words, 0, -1);
     return RB_OK;
 }
@@ -225,6 +223,8 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.n_chunks = (int)c->chunks.size();
     b.n_items = (long long)c->chunks.size() * c->lay.nbands;
     b.n_buckets = c->bucket_base[n];
+    b.gb_first = 0;
+    b.n_active = b.n_buckets;
     b.n_plane_words = c->plane_start[n];
     b.warm0 = WARMUP_WORDS;
     b.debug = c->params.reserved;
@@ -411,7 +411,6 @@ int rb_set_word_range(rb_ctx* c, int32_t word_first, int32_t word_last) {
     if (word_last < 0) word_last = nw;
     if (word_first < 0 || word_first > word_last || word_last > nw || (nw > 0 && word_first == word_last))
         return fail(c, RB_E_ARG, "rb_set_word_range: [%d, %d) is not a non-empty range of the contig's %d words", word_first, word_last, nw);
-    c->ranged = !(word_first == 0 && word_last == nw);
     make_chunks(c, std::max(1, word_last - word_first), word_first, word_last);
     size_items(c, nullptr);
     int rc;
@@ -419,6 +418,10 @@ int rb_set_word_range(rb_ctx* c, int32_t word_first, int32_t word_last) {
     c->batch.chunks = (const Chunk*)c->d_chunks.p;
     c->batch.n_chunks = (int)c->chunks.size();
     c->batch.n_items = (long long)c->chunks.size() * c->lay.nbands;
+    // the ordered compaction covers the buckets of the range; the tail bucket belongs to the part that ends at the last word
+    c->batch.gb_first = word_first;
+    c->batch.n_active = (word_last - word_first) + (word_last == nw ? 1 : 0);
+    c->batch.n_merge_blocks = (int)((c->batch.n_active + MERGE_BLOCK - 1) / MERGE_BLOCK);
     if ((rc = upload_items(c))) return rc;
     RB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->scanned = false;
@@ -452,8 +455,6 @@ int rb_scan_device(rb_ctx* c) {
     RB_CUDA(c, cudaEventRecord(c->ev[1], st));
     for (int attempt = 0;; ++attempt) {
         RB_CUDA(c, cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), st));
-        if (c->ranged)  // buckets outside the range are written by no chunk: they must read as empty
-            RB_CUDA(c, cudaMemsetAsync(b.meta, 0, (size_t)b.n_buckets * c->lay.nbands * sizeof(Meta), st));
         launch_scan(b, st);
         tm.launches += b.n_items ? 1 : 0;
         if (attempt == 0) RB_CUDA(c, cudaEventRecord(c->ev[2], st));

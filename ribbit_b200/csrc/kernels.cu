@@ -411,10 +411,10 @@ __device__ __forceinline__ void block_scan(const unsigned (&n)[3], const unsigne
 }
 
 __global__ void __launch_bounds__(MERGE_BLOCK) merge_count_kernel(DevBatch b) {
-    const long long gb = (long long)blockIdx.x * MERGE_BLOCK + threadIdx.x;
+    const long long gb = b.gb_first + (long long)blockIdx.x * MERGE_BLOCK + threadIdx.x;
     unsigned n[3] = {0u, 0u, 0u};
     unsigned long long e[2] = {0ull, 0ull};
-    if (gb < b.n_buckets) {
+    if (gb < b.gb_first + b.n_active) {
         const BucketInfo bi = bucket_info(b, gb);
         for (int s = 0; s < 3; ++s) n[s] = bi.n[s];
         e[0] = bi.emax[0]; e[1] = bi.emax[1];
@@ -493,8 +493,8 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     __shared__ int s_w[MERGE_BLOCK];
     __shared__ uint32_t s_wsum[MERGE_BLOCK / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long gb = (long long)blockIdx.x * MERGE_BLOCK + tid;
-    const bool live = gb < b.n_buckets;
+    const long long gb = b.gb_first + (long long)blockIdx.x * MERGE_BLOCK + tid;
+    const bool live = gb < b.gb_first + b.n_active;
     const int nbands = b.lay.nbands;
     BucketInfo bi;
     bi.c = 0; bi.w = 0;
@@ -542,9 +542,9 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     if (live) {
         long long o[3];
         for (int s = 0; s < 3; ++s) o[s] = (long long)bp.sum[s] + xs[s];
-        if (bi.w == 0)
+        if (bi.w == 0 || gb == b.gb_first)  // gb_first > 0: a word range of a single contig (rb_set_word_range)
             for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + bi.c] = o[s];
-        if (gb == b.n_buckets - 1)
+        if (gb == b.gb_first + b.n_active - 1)
             for (int s = 0; s < 3; ++s) b.contig_off[(long long)s * (b.n_contigs + 1) + b.n_contigs] = o[s] + bi.n[s];
         for (int s = 1; s < 3; ++s)
             if (bi.pseudo[s]) {

@@ -22,6 +22,8 @@ struct DevBatch {
     int n_chunks;
     long long n_items;        // n_chunks * nbands
     long long n_buckets;      // sum over contigs of nw + 1
+    long long gb_first;       // buckets the ordered compaction covers: [gb_first, gb_first + n_active); everything unless
+    long long n_active;       //   a word range of a single contig is scanned (rb_set_word_range)
     long long n_plane_words;  // plane words including guard words
     int warm0;
     int debug;                // bit 0: no tight loop, bit 1: no all-N chunk skip (diagnostics)

@@ -12,6 +12,8 @@ with tempfile.TemporaryDirectory() as td:
     fa = os.path.join(td, "x.fa"); synth.write_fasta(fa, [seq])
     out = {}
     arms = [("ribbit_gpu_nofilter", os.path.join(ROOT, "baseline/_ref/ribbit_gpu")), ("ribbit_gpu", os.path.join(ROOT, "baseline/_ref/ribbit_gpu"))]
+    if os.environ.get("EXP_CLI_SKIP_NOFILTER"):
+        arms = arms[1:]
     if os.path.exists(os.path.join(ROOT, "baseline/_ref/ribbit_gpu_hostmotif")):
         arms.append(("ribbit_gpu_hostmotif", os.path.join(ROOT, "baseline/_ref/ribbit_gpu_hostmotif")))
     arms.append(("ribbit_ref", os.path.join(ROOT, "oracle/_ref/ribbit_ref")))
