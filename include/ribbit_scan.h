@@ -11,6 +11,10 @@
  * merges addSeedToSeedPositions{Perfect,Substitutions,Anchored} (parse_perfect_shiftxor.cpp:47,
  * parse_substitute_shiftxor.cpp:18, parse_anchored_shiftxor.cpp:113). This library replaces everything up to that
  * hand-off: it returns, per contig, the three candidate streams in exactly the reference's call order.
+ * Around that path it also offers: rb_load_fasta (the reader loop of main, ribbit.cpp:269-280, on the device),
+ * rb_filter_seeds (the gate at the top of processSeed / processSeedMotifWise, parse_seed.cpp:344-367),
+ * rb_motif_rows (the row search of mostFrequentLongerMotif, parse_seed.cpp:153-256), rb_get_planes /
+ * rb_get_anchor_planes (the planes the host-side consumers read) and rb_set_word_range (one contig over several GPUs).
  *
  * There is no CPU fallback behind this ABI: rb_create fails when no CUDA device is usable.
  * Plain C types only; one context per GPU, one host thread per context.
