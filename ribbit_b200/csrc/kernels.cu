@@ -115,6 +115,19 @@ struct GpuSink {
 
 static const int SCAN_WARPS = 1;
 
+// fast -> slow transition (scan_core.h, lane_to_slow) out of line and with scalar arguments, so that the rare call does
+// not weigh on the register allocation of the scan loop
+__device__ __noinline__ bool slow_entry(uint32_t Ps, uint32_t r8s, uint32_t Pa, uint32_t r8a, uint32_t x_prev, int lastRS, int w,
+                                        SlowEntry& e) {
+    EvCarry cs, ca;
+    cs.P = Ps; cs.r8 = r8s; ca.P = Pa; ca.r8 = r8a;
+    SlowEntry t;
+    if (!win_from_fast(cs, 32 * (w - 1), t.S) || !win_from_fast(ca, 32 * (w - 1), t.A)) return false;
+    t.pst = (x_prev >> 31) ? lastRS : -1;
+    e = t;
+    return true;
+}
+
 template <int BW>
 #ifndef RB_SCAN_BLOCKS_PER_SM
 #define RB_SCAN_BLOCKS_PER_SM 20
@@ -250,15 +263,29 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             }
         }
         int slow = active ? ((force && w < we) || !word_is_fast(cw, w, cg.nw)) : 1;
-        if (active && slow && !prev_slow) {
-            // fast -> slow: the reference machines' state is rebuilt by a warm-up that ends here
-            we = w; nb = w; H = b.warm0; force = 1;
-            q = warmup_start(we, nb, H);
-            Ha = warmup_anchor_words(q, H);
-            lane_init(cfg, st, cw, q);
-            w = q;
-            prev_slow = 1;
-            slow = 1;
+        {
+            // fast -> slow: the reference machines' state comes from the bit-parallel view of the previous word when every
+            // lane's word holds nine failing windows in a row (lane_to_slow), else it is rebuilt by a warm-up that ends here
+            const bool trans = active && slow && !prev_slow;
+            SlowEntry se;
+            se.S = st.S; se.A = st.A; se.pst = st.pst;
+            bool conv_ok = true;
+            if (trans && cfg.motif) conv_ok = slow_entry(st.es.P, st.es.r8, st.ea.P, st.ea.r8, st.x_prev, st.lastRS, w, se);
+            const unsigned conv_fail = __ballot_sync(0xFFFFFFFFu, !conv_ok) & gmask;
+            if (trans) {
+                if (!conv_fail) {
+                    lane_enter_slow(st, se);
+                    prev_slow = 1;
+                } else {
+                    we = w; nb = w; H = b.warm0; force = 1;
+                    q = warmup_start(we, nb, H);
+                    Ha = warmup_anchor_words(q, H);
+                    lane_init(cfg, st, cw, q);
+                    w = q;
+                    prev_slow = 1;
+                    slow = 1;
+                }
+            }
         }
         uint32_t a = 0u;
         if (active) a = slow ? lane_phase1(cfg, st, cw, w, L) : lane_phase1_fast(cfg, st, cw, w, L);

@@ -431,6 +431,47 @@ RB_HD void win_to_fast(const WinState& st, int& lastS) {
     else if (st.cur != -1) lastS = st.cur + 7;
 }
 
+// fast word -> slow word: the reference machine's state at the end of fast word w-1 (p0 = 32*(w-1)) from the bit-parallel
+// view of that word: c.P = its pass mask, c.r8 = "eight failing windows in a row end here". After NINE failing windows in
+// a row the machine is idle (the pending component was emitted at the ninth, parse_substitute_shiftxor.cpp:500-530); the
+// windows of the word behind the last such point are run through the machine without emitting (the fast path emitted
+// them). Returns false when the word holds no nine failing windows in a row: the caller rebuilds the state by a warm-up.
+RB_HD bool win_from_fast(const EvCarry& c, int p0, WinState& st) {
+    const uint32_t n9 = c.r8 & (c.r8 << 1);
+    if (!n9) return false;
+    st.cur = st.ls = st.le = -1;
+    for (int i = 32 - clz32(n9); i < 32; ++i) {
+        const int wp = p0 + i - 7;
+        if ((c.P >> i) & 1u) {
+            if (st.cur == -1) {
+                st.cur = wp;
+                if (st.le != -1 && st.le < st.cur) { st.ls = -1; st.le = -1; }
+            }
+        } else if (st.cur != -1) {
+            if (st.ls == -1) st.ls = st.cur;
+            st.le = wp + 7;
+            st.cur = -1;
+        } else if (st.le != -1 && st.le < wp) {
+            st.ls = -1; st.le = -1;
+        }
+    }
+    return true;
+}
+// All three machines of a motif lane at a fast -> slow transition in front of word w (x_prev = X_m[w-1] already rotated).
+// The new state is returned apart from the lane state: the caller applies it only if every lane of the item succeeded.
+struct SlowEntry {
+    WinState S, A;
+    int pst;
+};
+RB_HD bool lane_to_slow(const LaneCfg& cfg, const LaneState& st, int w, SlowEntry& e) {
+    e.S = st.S; e.A = st.A; e.pst = st.pst;
+    if (!cfg.motif) return true;
+    if (!win_from_fast(st.es, 32 * (w - 1), e.S) || !win_from_fast(st.ea, 32 * (w - 1), e.A)) return false;
+    e.pst = (st.x_prev >> 31) ? st.lastRS : -1;  // the run that is open at the word boundary (parse_perfect_shiftxor.cpp:194)
+    return true;
+}
+RB_HD void lane_enter_slow(LaneState& st, const SlowEntry& e) { st.S = e.S; st.A = e.A; st.pst = e.pst; }
+
 // "six ones in a row ending at t" of X_m, with carries; kept up to date in every word (fast and slow)
 RB_HD uint32_t six_ones(uint32_t x, uint32_t xs1, uint32_t& pa2, uint32_t& pa6) {
     const uint32_t a2 = x & xs1;

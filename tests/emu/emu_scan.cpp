@@ -128,10 +128,20 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                     }
                     const int slow = (force && w < we) || !word_is_fast(cw, w, nw);
                     if (slow && !prev_slow) {
-                        // fast -> slow: the reference machines' state is rebuilt by a warm-up that ends here
-                        we = w; nb = w; H = warm0; force = 1; replay = true;
-                        if (replays) ++*replays;
-                        break;
+                        // fast -> slow: the reference machines' state comes from the bit-parallel view of the previous word
+                        // when every lane's word holds nine failing windows in a row ...
+                        bool ok = true;
+                        SlowEntry se[32];
+                        for (int j = 0; j < lay.bw; ++j) ok = lane_to_slow(cfg[j], st[j], w, se[j]) && ok;
+                        if (ok) {
+                            for (int j = 0; j < lay.bw; ++j) lane_enter_slow(st[j], se[j]);
+                            prev_slow = 1;
+                        } else {
+                            // ... else it is rebuilt by a warm-up that ends here
+                            we = w; nb = w; H = warm0; force = 1; replay = true;
+                            if (replays) ++*replays;
+                            break;
+                        }
                     }
                     uint32_t a[32 + 4] = {0};
                     for (int j = 0; j < lay.bw; ++j)
