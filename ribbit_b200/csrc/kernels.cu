@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             const bool trans = active && slow && !prev_slow;
             SlowEntry se;
             se.S = st.S; se.A = st.A; se.pst = st.pst;
-            bool conv_ok = true;
-            if (trans && cfg.motif) conv_ok = slow_entry(st.es.P, st.es.r8, st.ea.P, st.ea.r8, st.x_prev, st.lastRS, w, se);
+            bool conv_ok = !trans || w >= q + Ha;  // the machines run in this word (not an anchors-only warm-up word)
+            if (trans && conv_ok && cfg.motif) conv_ok = slow_entry(st.es.P, st.es.r8, st.ea.P, st.ea.r8, st.x_prev, st.lastRS, w, se);
             const unsigned conv_fail = __ballot_sync(0xFFFFFFFFu, !conv_ok) & gmask;
             if (trans) {
                 if (!conv_fail) {

@@ -130,7 +130,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                     if (slow && !prev_slow) {
                         // fast -> slow: the reference machines' state comes from the bit-parallel view of the previous word
                         // when every lane's word holds nine failing windows in a row ...
-                        bool ok = true;
+                        bool ok = w >= q + Ha;  // the machines run in this word (not an anchors-only warm-up word)
                         SlowEntry se[32];
                         for (int j = 0; j < lay.bw; ++j) ok = lane_to_slow(cfg[j], st[j], w, se[j]) && ok;
                         if (ok) {

@@ -74,3 +74,38 @@ def test_emulator_chunks_inside_long_n_runs_skip_instead_of_rescanning():
                 skips += emu_util.emu_streams.last_skips
                 _same(got, exp)
             assert skips > 0
+
+
+def _regress_cases():
+    import glob
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regress")
+    for f in sorted(glob.glob(os.path.join(d, "*.txt"))):
+        hdr, seq = open(f, "rb").read().split(b"\n", 1)
+        mlo, mhi, cw = map(int, hdr.split())
+        yield os.path.basename(f), seq, mlo, mhi, cw
+
+
+def test_emulator_regression_cases():
+    """Inputs a GPU fuzz campaign once got wrong (tests/golden/regress: first line = min_mlen max_mlen chunk_words): a
+    fast -> slow transition inside an anchors-only warm-up word must not take the machine state from the fast view."""
+    n = 0
+    for name, seq, mlo, mhi, cw in _regress_cases():
+        exp = sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi))
+        for c in {cw if cw else 1 << 30, 1, 2, 3}:
+            got, _ = emu_util.emu_streams(seq, mlo, mhi, c)
+            _same(got, exp)
+        n += 1
+    assert n >= 3
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_emulator_tiny_chunks_fuzz(seed):
+    """Chunks of 1-3 words: every chunk start is a warm-up, transitions fall into warm-ups."""
+    rng = np.random.default_rng(1000 + seed)
+    for L, nd, mlo, mhi in ((2000, 0.01, 5, 30), (2000, 0.05, 2, 100), (1500, 0.01, 40, 100), (2500, 0.003, 2, 24)):
+        seq = synth.fuzz_contig(rng, L, nd, m_range=(mlo, min(mhi, 60)))
+        exp = sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi))
+        for cw in (1, 2, 3):
+            got, _ = emu_util.emu_streams(seq, mlo, mhi, cw)
+            _same(got, exp)

@@ -356,3 +356,24 @@ def test_contig_split_over_word_ranges():
         sc.load([seq, seq[:100]])
         with pytest.raises(scan.RibbitScanError):
             sc.set_word_range(0, 1)
+
+
+@pytest.mark.gpu
+def test_regression_cases_tiny_chunks():
+    """tests/golden/regress (inputs a fuzz campaign once got wrong) and tiny chunk sizes through the C ABI."""
+    import glob
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regress")
+    files = sorted(glob.glob(os.path.join(d, "*.txt")))
+    assert len(files) >= 3
+    for f in files:
+        hdr, seq = open(f, "rb").read().split(b"\n", 1)
+        mlo, mhi, cw = map(int, hdr.split())
+        exp = sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi))
+        for c in sorted({cw, 1, 2, 3}):
+            sc = scan.Scanner(mlo, mhi, chunk_words=c)
+            sc.load([seq])
+            got = scan.contig_streams(sc.scan(), 0)
+            sc.close()
+            for s in (1, 2, 3):
+                assert got[s].shape == exp[s].shape and (got[s] == exp[s]).all(), (os.path.basename(f), c, s)
