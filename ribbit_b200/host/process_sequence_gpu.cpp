@@ -12,14 +12,24 @@
 // No scan happens on the CPU here: without a usable CUDA device the program stops with an error.
 #include <boost/dynamic_bitset.hpp>
 
+#include <poll.h>
+#include <sys/mman.h>
+#include <sys/socket.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <cerrno>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <atomic>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <tuple>
 #include <unordered_map>
+#include <algorithm>
 #include <vector>
 
 #include "bitseq_utils.h"
@@ -116,6 +126,112 @@ Bitset to_bitset(const uint32_t *w, long L) {
     return b;
 }
 
+// ---- per-seed stage on several host cores ------------------------------------------------------------------------------
+// processSeed / processSeedMotifWise keep their scratch state in globals (global_variables.h: MOTIF_*, REPEAT_CLASSES), so
+// they cannot run on threads; they can run in forked worker processes: every global scratch slot is re-initialised on first
+// touch inside a call (parse_smallmotif_seed.cpp:103-116), REPEAT_CLASSES memoises a pure function (bitseq_utils.cpp:195-217),
+// so a seed's rows do not depend on the seeds processed before it. Workers claim parts of the seed list from a shared
+// counter, write the BED rows of a part into a buffer, and hand the buffers back through an unlinked temp file; the parent
+// emits the parts in order. A CUDA context does not survive fork(), so the parent keeps the GPU and serves the workers'
+// single-seed rb_motif_rows requests (recursive flank seeds, parse_seed.cpp:443-463) over a socket pair.
+int g_worker_fd = -1;
+
+bool write_all(int fd, const void *p, size_t n) {
+    const char *c = (const char *)p;
+    while (n) {
+        const ssize_t k = write(fd, c, n);
+        if (k < 0) { if (errno == EINTR) continue; return false; }
+        c += k; n -= (size_t)k;
+    }
+    return true;
+}
+bool read_all(int fd, void *p, size_t n) {
+    char *c = (char *)p;
+    while (n) {
+        const ssize_t k = read(fd, c, n);
+        if (k == 0) return false;
+        if (k < 0) { if (errno == EINTR) continue; return false; }
+        c += k; n -= (size_t)k;
+    }
+    return true;
+}
+
+int host_procs() {
+    const char *env = getenv("RIBBIT_HOST_PROCS");
+    const int n = env ? atoi(env) : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    return std::max(1, n);
+}
+
+// Runs body(part, stream) for part = 0..n_parts-1 in `procs` forked workers and writes the parts' output to `out` in part
+// order. serve(fd): the parent's answer to one request arriving on a worker's socket (returns false on EOF).
+template <class Body, class Serve>
+void forked_parts(int n_parts, int procs, ostream &out, Body body, Serve serve) {
+    std::atomic<int> *next = (std::atomic<int> *)mmap(nullptr, sizeof(std::atomic<int>), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (next == MAP_FAILED) { cerr << "ERROR: mmap: " << strerror(errno) << "\n"; exit(1); }
+    new (next) std::atomic<int>(0);
+    out.flush();
+    cerr.flush();
+    vector<pid_t> pids((size_t)procs);
+    vector<int> socks((size_t)procs), files((size_t)procs);
+    const char *tmpdir = getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp";
+    for (int w = 0; w < procs; ++w) {
+        int sv[2];
+        string path = string(tmpdir) + "/ribbit_gpu.XXXXXX";
+        files[(size_t)w] = mkstemp(&path[0]);
+        if (files[(size_t)w] < 0 || socketpair(AF_UNIX, SOCK_STREAM, 0, sv) != 0) { cerr << "ERROR: worker set-up: " << strerror(errno) << "\n"; exit(1); }
+        unlink(path.c_str());
+        const pid_t pid = fork();
+        if (pid < 0) { cerr << "ERROR: fork: " << strerror(errno) << "\n"; exit(1); }
+        if (pid == 0) {  // worker: never touches CUDA, never returns
+            close(sv[0]);
+            for (int v = 0; v < w; ++v) close(socks[(size_t)v]);
+            g_worker_fd = sv[1];
+            for (int part = (*next)++; part < n_parts; part = (*next)++) {
+                std::ostringstream os;
+                body(part, os);
+                const string text = os.str();
+                const int64_t hdr[2] = {part, (int64_t)text.size()};
+                if (!write_all(files[(size_t)w], hdr, sizeof hdr) || !write_all(files[(size_t)w], text.data(), text.size())) _exit(4);
+            }
+            _exit(0);
+        }
+        close(sv[1]);
+        pids[(size_t)w] = pid;
+        socks[(size_t)w] = sv[0];
+    }
+    // parent: serve GPU requests until every worker has closed its socket
+    vector<pollfd> pf((size_t)procs);
+    int open_socks = procs;
+    for (int w = 0; w < procs; ++w) { pf[(size_t)w].fd = socks[(size_t)w]; pf[(size_t)w].events = POLLIN; }
+    while (open_socks > 0) {
+        if (poll(pf.data(), (nfds_t)procs, -1) < 0) { if (errno == EINTR) continue; cerr << "ERROR: poll: " << strerror(errno) << "\n"; exit(1); }
+        for (int w = 0; w < procs; ++w)
+            if (pf[(size_t)w].fd >= 0 && (pf[(size_t)w].revents & (POLLIN | POLLHUP | POLLERR)))
+                if (!serve(pf[(size_t)w].fd)) { close(pf[(size_t)w].fd); pf[(size_t)w].fd = -1; --open_socks; }
+    }
+    bool ok = true;
+    for (int w = 0; w < procs; ++w) {
+        int status = 0;
+        while (waitpid(pids[(size_t)w], &status, 0) < 0 && errno == EINTR) {}
+        if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) ok = false;
+    }
+    if (!ok) { cerr << "ERROR: a per-seed worker process failed\n"; exit(1); }
+    vector<string> parts((size_t)n_parts);
+    for (int w = 0; w < procs; ++w) {
+        const int fd = files[(size_t)w];
+        lseek(fd, 0, SEEK_SET);
+        int64_t hdr[2];
+        while (read_all(fd, hdr, sizeof hdr)) {
+            string &t = parts[(size_t)hdr[0]];
+            t.resize((size_t)hdr[1]);
+            if (hdr[1] && !read_all(fd, &t[0], (size_t)hdr[1])) { cerr << "ERROR: truncated worker output\n"; exit(1); }
+        }
+        close(fd);
+    }
+    for (const string &t : parts) out << t;
+    munmap((void *)next, sizeof(std::atomic<int>));
+}
+
 #ifndef RIBBIT_HOST_MOTIF
 // K7: rows chosen by the consensus-motif search (rb_motif_rows) for the top-level seeds of the current contig, computed in
 // one batch before the per-seed walk. key = seed_start | mlen << 32; value = {seed_sequence_length, row}.
@@ -142,7 +258,9 @@ uint256_t mostFrequentLongerMotif(Bitset &left_bset, Bitset &right_bset, int &se
     } else {
         const rb_seed sd = {0, seed_start, seed_start + seed_sequence_length, motif_length};
         rb_motifrow r;
-        if (rb_motif_rows(g_gpu.ctx, &sd, 1, &r) != RB_OK) die("rb_motif_rows", g_gpu.ctx);
+        if (g_worker_fd >= 0) {  // worker process of the per-seed stage: the parent owns the GPU
+            if (!write_all(g_worker_fd, &sd, sizeof sd) || !read_all(g_worker_fd, &r, sizeof r)) { cerr << "ERROR: worker lost its parent\n"; _exit(3); }
+        } else if (rb_motif_rows(g_gpu.ctx, &sd, 1, &r) != RB_OK) die("rb_motif_rows", g_gpu.ctx);
         row = r.row; ++g_motif.misses;
     }
     uint256_t unit = 0;
@@ -336,20 +454,53 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
             g_motif.rows.emplace(MotifRows::key(mseeds[k].start, mseeds[k].mlen), std::make_pair(mseeds[k].end - mseeds[k].start, mrows[k].row));
     }
 #endif
-    for (size_t k = 0; k < todo.size(); ++k) {
-        if (use_filter && info[k].longest_run < continuous_ones_threshold) continue;
-        int mlen = todo[k].mlen, rank = todo_rank[k];
-        const int from = todo[k].start, to = todo[k].end;
-        Bitset &plane = lshift_xor_bsets[mlen - MINIMUM_SHIFT];
-        if (mlen <= 10)
-            processSeedMotifWise(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset,
-                                 right_bset, N_bset, continuous_ones_threshold, out, aligner, filter, alignment);
-        else
-            processSeed(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset, right_bset,
-                        N_bset, continuous_ones_threshold, out, MATRIX, aligner, filter, alignment);
-    }
+    vector<size_t> live;  // seeds that are handed to the per-seed functions, in processing order
+    for (size_t k = 0; k < todo.size(); ++k)
+        if (!(use_filter && info[k].longest_run < continuous_ones_threshold)) live.push_back(k);
+    auto run_seeds = [&](size_t i0, size_t i1, ostream &o) {
+        for (size_t i = i0; i < i1; ++i) {
+            const size_t k = live[i];
+            int mlen = todo[k].mlen, rank = todo_rank[k];
+            const int from = todo[k].start, to = todo[k].end;
+            Bitset &plane = lshift_xor_bsets[mlen - MINIMUM_SHIFT];
+            if (mlen <= 10)
+                processSeedMotifWise(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset,
+                                     right_bset, N_bset, continuous_ones_threshold, o, aligner, filter, alignment);
+            else
+                processSeed(tuple<int, int>{from, to}, mlen, rank, sequence_id, sequence, sequence_length, plane, left_bset, right_bset,
+                            N_bset, continuous_ones_threshold, o, MATRIX, aligner, filter, alignment);
+        }
+    };
+    const int procs = host_procs();
+    long served = 0;
 #ifndef RIBBIT_HOST_MOTIF
-    if (getenv("RIBBIT_VERBOSE")) cerr << "K7 motif rows: " << g_motif.hits << " from the batch, " << g_motif.misses << " single calls\n";
+    if (procs > 1 && live.size() >= 4096) {
+        // parts of roughly equal work (seed length + motif size as the weight), several per worker
+        const int n_parts = (int)std::min<size_t>((size_t)procs * 8, live.size() / 256);
+        vector<double> acc(live.size() + 1, 0.0);
+        for (size_t i = 0; i < live.size(); ++i) acc[i + 1] = acc[i] + 64.0 + (todo[live[i]].end - todo[live[i]].start) + todo[live[i]].mlen;
+        vector<size_t> cut((size_t)n_parts + 1, live.size());
+        cut[0] = 0;
+        for (int p = 1; p < n_parts; ++p)
+            cut[(size_t)p] = (size_t)(std::lower_bound(acc.begin(), acc.end(), acc.back() * p / n_parts) - acc.begin());
+        for (int p = 1; p <= n_parts; ++p) cut[(size_t)p] = std::max(cut[(size_t)p], cut[(size_t)p - 1]);
+        forked_parts(n_parts, procs, out,
+                     [&](int part, ostream &o) { run_seeds(cut[(size_t)part], cut[(size_t)part + 1], o); },
+                     [&](int fd) {
+                         rb_seed sd;
+                         if (!read_all(fd, &sd, sizeof sd)) return false;
+                         rb_motifrow r;
+                         if (rb_motif_rows(ctx, &sd, 1, &r) != RB_OK) die("rb_motif_rows", ctx);
+                         ++served;
+                         return write_all(fd, &r, sizeof r);
+                     });
+    } else
+#endif
+        run_seeds(0, live.size(), out);
+#ifndef RIBBIT_HOST_MOTIF
+    if (getenv("RIBBIT_VERBOSE"))
+        cerr << "K7 motif rows: " << g_motif.rows.size() << " in the batch, " << g_motif.misses + served << " single calls; per-seed stage on "
+             << ((procs > 1 && live.size() >= 4096) ? procs : 1) << " process(es)\n";
 #endif
     cerr << "Total number of seeds that are processed for alignment: " << processed_seeds << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
 }
