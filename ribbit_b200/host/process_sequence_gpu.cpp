@@ -19,6 +19,7 @@
 #include <unistd.h>
 
 #include <cerrno>
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -156,6 +157,17 @@ bool read_all(int fd, void *p, size_t n) {
     return true;
 }
 
+// RIBBIT_VERBOSE=1: wall time of every stage of processSequence on stderr
+struct StageClock {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    const bool on = getenv("RIBBIT_VERBOSE") != nullptr;
+    void mark(const char *what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (on) cerr << "  [stage] " << what << ": " << std::chrono::duration<double>(now - t).count() << " s\n";
+        t = now;
+    }
+};
+
 int host_procs() {
     const char *env = getenv("RIBBIT_HOST_PROCS");
     const int n = env ? atoi(env) : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
@@ -277,8 +289,10 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
                      int continuous_ones_threshold, ostream &out) {
     (void)window_length; (void)window_bitcount_threshold; (void)anchor_size;  // fixed in the reference: 8, 7 then 6, 3
     START_TIME = time(0);
+    StageClock clock;
     int sequence_length = (int)sequence.length();
     rb_ctx *ctx = gpu_context();
+    clock.mark("GPU context");
 
     // ---- the scan, on the GPU: K1 pack, K2 scan, K6 ordered streams -------------------------------------------
     const int64_t off0 = 0;
@@ -286,6 +300,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     if (rb_load_contigs(ctx, sequence.data(), &off0, &len0, 1) != RB_OK) die("rb_load_contigs", ctx);
     rb_streams st;
     if (rb_scan(ctx, &st) != RB_OK) die("rb_scan", ctx);
+    clock.mark("load + scan + fetch");
     cerr << "Generated shift XORs!\t Time elapsed:" << difftime(time(0), START_TIME) << "secs\n";
 
     // ---- planes for the host-side consumers (merge tie-breakers read popcounts of the match planes) -----------
@@ -319,6 +334,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
         lshift_xor_bsets[(size_t)k] = ~(left_bset ^ (left_bset << (i))) & ~(right_bset ^ (right_bset << (i)));
     });
 
+    clock.mark("code + match planes as bitsets");
     SeedList seed_positions_perfect, seed_positions_substut, seed_positions_anchored;
     const int bset_size = sequence_length;
 
@@ -367,6 +383,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
             lshift_xor_bsets[m - MINIMUM_SHIFT] = bm;
         });
     }
+    clock.mark("perfect + substitution merges, anchor planes");
     cerr << "Generated anchored shift XORs!\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
 
     // ---- anchored candidates (parse_anchored_shiftxor.cpp:595…717) -----------------------------------------------
@@ -411,6 +428,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     // ---- per-seed stage (what fasta_utils.cpp:174-246 does): the three lists are walked head to head, the head with
     // the smallest start goes first (ties: perfect, then substitution, then anchored); entries re-tagged -1 by the
     // merges are skipped; seeds shorter than 0.9 motif lengths are not processed -----------------------------------
+    clock.mark("anchored merge");
     StripedSmithWaterman::Aligner aligner;
     StripedSmithWaterman::Filter filter;
     StripedSmithWaterman::Alignment alignment;
@@ -471,6 +489,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
                             N_bset, continuous_ones_threshold, o, MATRIX, aligner, filter, alignment);
         }
     };
+    clock.mark("seed gate (K5) + motif rows (K7)");
     const int procs = host_procs();
     long served = 0;
 #ifndef RIBBIT_HOST_MOTIF
@@ -497,6 +516,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     } else
 #endif
         run_seeds(0, live.size(), out);
+    clock.mark("per-seed stage");
 #ifndef RIBBIT_HOST_MOTIF
     if (getenv("RIBBIT_VERBOSE"))
         cerr << "K7 motif rows: " << g_motif.rows.size() << " in the batch, " << g_motif.misses + served << " single calls; per-seed stage on "

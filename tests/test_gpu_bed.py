@@ -93,3 +93,12 @@ def test_mbp_scale_bed_digest_matches_the_reference(name):
         assert len(lists) == c["cp2_rows"] and hashlib.md5(lists.astype("<i4").tobytes()).hexdigest() == c["cp2_md5"]
         b = open(bed, "rb").read()
         assert b.count(b"\n") == c["bed_rows"] and hashlib.md5(b).hexdigest() == c["bed_md5"]
+        if name == "c2_1mbp_nruns":
+            # the per-seed stage runs in forked worker processes by default: one process and an odd number of workers give
+            # the same bytes
+            for procs in ("1", "3"):
+                r = subprocess.run([EXE, "-i", fa, "-o", bed, *c["flags"]], env=dict(os.environ, RIBBIT_HOST_PROCS=procs, RIBBIT_VERBOSE="1"),
+                                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=1200)
+                assert r.returncode == 0, r.stderr[-500:]
+                assert ("per-seed stage on %s process" % procs).encode() in r.stderr
+                assert open(bed, "rb").read() == b
