@@ -329,13 +329,13 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             // word `we` (state check) and the first fast words of a stretch (keep filter not yet trusted) go through the
             // general path; the tight loop stops before the contig's tail zone (anchor view differs from X_s there)
             if (active && !badmask && w > we && w >= e0 && fastrun >= 4 && !prev_slow && !(b.debug & 1)) {
-                uint32_t vprev = cw[w - 1].v;
+                uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
                 const int wend = min(min(ch.w1, cg.nw - 1), ((L - b.lay.s_hi) >> 5) - 1);
+                Meta* mp = meta + w;
                 while (w < wend) {
-                    const uint32_t vcur = cw[w].v;
                     if ((vprev & vcur) != 0xFFFFFFFFu) break;
-                    vprev = vcur;
-                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L);
+                    uint32_t vnext;  // v of word w + 1, from the plane word phase 1 loads anyway
+                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L, &vnext);
                     uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
                     uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
                     IterCtx it;
@@ -344,8 +344,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
                     lane_phase2_fast(sk, cfg, st, it, f_m2, f_m1, f_p1, f_p2);
                     const uint32_t counts = __reduce_add_sync(0xFFFFFFFFu, sk.counts);
                     const int dS = __reduce_max_sync(0xFFFFFFFFu, sk.dS), dA = __reduce_max_sync(0xFFFFFFFFu, sk.dA);
-                    if (j == 0) meta[w] = make_meta(counts, dS, dA, 0, off);
+                    if (j == 0) *mp = make_meta(counts, dS, dA, 0, off);
+                    ++mp;
                     off += (counts & 0x3FFu) + ((counts >> 10) & 0x3FFu) + (counts >> 20);
+                    vprev = vcur; vcur = vnext;
                     ++w;
                 }
             }

@@ -189,6 +189,16 @@ RB_HD uint32_t x_word_next(const PlaneWord* cw, int w, int s, XCache& xc) {
     return ~(th | tl);
 }
 
+// same with the unshifted plane word o = cw[w] already loaded by the caller
+RB_HD uint32_t x_word_next_o(const PlaneWord& o, const PlaneWord* cw, int w, int s, XCache& xc) {
+    const int off = s >> 5, sh = s & 31;
+    const PlaneWord b = cw[w + off + 1];
+    const uint32_t th = o.h ^ fsr(xc.h, b.h, sh);
+    const uint32_t tl = o.l ^ fsr(xc.l, b.l, sh);
+    xc.h = b.h; xc.l = b.l; xc.idx = w + off + 1;
+    return ~(th | tl);
+}
+
 // positions p >= L - s never close an anchor run (parse_anchored_shiftxor.cpp:37): force them to 1 so that the
 // run that reaches L-1-s looks unbounded and is dropped by the "< 2*s" test.
 RB_HD uint32_t anchor_endmask(int w, int L, int s) {
@@ -571,9 +581,17 @@ RB_HD uint32_t lane_phase1(const LaneCfg& cfg, LaneState& st, const PlaneWord* c
 // this word can reach 2s positions and the word is not near the contig end; then A_s[w] = the positions of X_s that
 // lie in a run of at least 3 (anchor_size, parse_anchored_shiftxor.cpp:44). Everything else takes anchor_word.
 template <bool SEQ>
-RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
-    if (cfg.s == 0) return 0u;
-    st.x_nxt = SEQ ? x_word_next(cw, w + 1, cfg.s, st.xc) : x_word_cached(cw, w + 1, cfg.s, st.xc);
+RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t* v_next = nullptr) {
+    if (SEQ) {
+        // every lane (idle ones too) reads the same word w+1: its v field is the caller's fast-word test for the next step
+        const PlaneWord o = cw[w + 1];
+        if (v_next) *v_next = o.v;
+        if (cfg.s == 0) return 0u;
+        st.x_nxt = x_word_next_o(o, cw, w + 1, cfg.s, st.xc);
+    } else {
+        if (cfg.s == 0) return 0u;
+        st.x_nxt = x_word_cached(cw, w + 1, cfg.s, st.xc);
+    }
     const uint32_t x = st.x_cur, xn = st.x_nxt, xp = st.x_prev;
     const int K2 = 2 * cfg.s;
     // SEQ: the caller keeps w + 1 below every lane's wm
@@ -621,8 +639,8 @@ RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWo
     return lane_phase1_fast_t<false>(cfg, st, cw, w, L);
 }
 // the previous call (either phase-1 variant) was for word w-1
-RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L) {
-    return lane_phase1_fast_t<true>(cfg, st, cw, w, L);
+RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t* v_next = nullptr) {
+    return lane_phase1_fast_t<true>(cfg, st, cw, w, L, v_next);
 }
 
 // Phase 2 of a fast word (it.slow == 0, machines on) (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so
