@@ -332,10 +332,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
                 uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
                 const int wend = min(min(ch.w1, cg.nw - 1), ((L - b.lay.s_hi) >> 5) - 1);
                 Meta* mp = meta + w;
+                SeqPtrs sp;
+                sp.o = cw + (w + 1);
+                sp.b = cw + (w + 1 + (cfg.s >> 5) + 1);
+                const int w_in = w;
                 while (w < wend) {
                     if ((vprev & vcur) != 0xFFFFFFFFu) break;
                     uint32_t vnext;  // v of word w + 1, from the plane word phase 1 loads anyway
-                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L, &vnext);
+                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L, vnext, sp);
                     uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
                     uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
                     IterCtx it;
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
                     vprev = vcur; vcur = vnext;
                     ++w;
                 }
+                if (w != w_in && cfg.s) st.xc.idx = w + (cfg.s >> 5) + 1;  // the cached plane word: the last b operand
             }
         }
     }

@@ -189,15 +189,19 @@ RB_HD uint32_t x_word_next(const PlaneWord* cw, int w, int s, XCache& xc) {
     return ~(th | tl);
 }
 
-// same with the unshifted plane word o = cw[w] already loaded by the caller
-RB_HD uint32_t x_word_next_o(const PlaneWord& o, const PlaneWord* cw, int w, int s, XCache& xc) {
-    const int off = s >> 5, sh = s & 31;
-    const PlaneWord b = cw[w + off + 1];
+// same with both plane words already loaded by the caller: o = cw[w], b = cw[w + (s >> 5) + 1]; xc.idx is left to the caller
+RB_HD uint32_t x_word_next_ob(const PlaneWord& o, const PlaneWord& b, int s, XCache& xc) {
+    const int sh = s & 31;
     const uint32_t th = o.h ^ fsr(xc.h, b.h, sh);
     const uint32_t tl = o.l ^ fsr(xc.l, b.l, sh);
-    xc.h = b.h; xc.l = b.l; xc.idx = w + off + 1;
+    xc.h = b.h; xc.l = b.l;
     return ~(th | tl);
 }
+// running pointers of the tight loop: o = &cw[w + 1] (the same for all lanes), b = &cw[w + 1 + (s >> 5) + 1] (per lane)
+struct SeqPtrs {
+    const PlaneWord* o;
+    const PlaneWord* b;
+};
 
 // positions p >= L - s never close an anchor run (parse_anchored_shiftxor.cpp:37): force them to 1 so that the
 // run that reaches L-1-s looks unbounded and is dropped by the "< 2*s" test.
@@ -581,13 +585,15 @@ RB_HD uint32_t lane_phase1(const LaneCfg& cfg, LaneState& st, const PlaneWord* c
 // this word can reach 2s positions and the word is not near the contig end; then A_s[w] = the positions of X_s that
 // lie in a run of at least 3 (anchor_size, parse_anchored_shiftxor.cpp:44). Everything else takes anchor_word.
 template <bool SEQ>
-RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t* v_next = nullptr) {
+RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t* v_next = nullptr,
+                                  SeqPtrs* sp = nullptr) {
     if (SEQ) {
         // every lane (idle ones too) reads the same word w+1: its v field is the caller's fast-word test for the next step
-        const PlaneWord o = cw[w + 1];
-        if (v_next) *v_next = o.v;
+        const PlaneWord o = *sp->o, b = *sp->b;
+        ++sp->o; ++sp->b;
+        *v_next = o.v;
         if (cfg.s == 0) return 0u;
-        st.x_nxt = x_word_next_o(o, cw, w + 1, cfg.s, st.xc);
+        st.x_nxt = x_word_next_ob(o, b, cfg.s, st.xc);
     } else {
         if (cfg.s == 0) return 0u;
         st.x_nxt = x_word_cached(cw, w + 1, cfg.s, st.xc);
@@ -639,8 +645,9 @@ RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWo
     return lane_phase1_fast_t<false>(cfg, st, cw, w, L);
 }
 // the previous call (either phase-1 variant) was for word w-1
-RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t* v_next = nullptr) {
-    return lane_phase1_fast_t<true>(cfg, st, cw, w, L, v_next);
+// (tight loop; the caller owns the running pointers and restores st.xc.idx when it leaves the loop)
+RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t& v_next, SeqPtrs& sp) {
+    return lane_phase1_fast_t<true>(cfg, st, cw, w, L, &v_next, &sp);
 }
 
 // Phase 2 of a fast word (it.slow == 0, machines on) (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so
