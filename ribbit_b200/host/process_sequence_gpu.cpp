@@ -177,27 +177,45 @@ int host_procs() {
 // Runs body(part, stream) for part = 0..n_parts-1 in `procs` forked workers and writes the parts' output to `out` in part
 // order. serve(fd): the parent's answer to one request arriving on a worker's socket (returns false on EOF).
 template <class Body, class Serve>
-void forked_parts(int n_parts, int procs, ostream &out, Body body, Serve serve) {
-    std::atomic<int> *next = (std::atomic<int> *)mmap(nullptr, sizeof(std::atomic<int>), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
-    if (next == MAP_FAILED) { cerr << "ERROR: mmap: " << strerror(errno) << "\n"; exit(1); }
+bool forked_parts(int n_parts, int procs, ostream &out, Body body, Serve serve) {
+    // everything a worker needs is set up before the first fork; if the system refuses (no temp dir, descriptor or process
+    // limit) the caller runs the stage in-process
+    const char *tmpdir = getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp";
+    vector<int> files((size_t)procs, -1), sock_parent((size_t)procs, -1), sock_child((size_t)procs, -1);
+    bool setup = true;
+    for (int w = 0; w < procs && setup; ++w) {
+        string path = string(tmpdir) + "/ribbit_gpu.XXXXXX";
+        files[(size_t)w] = mkstemp(&path[0]);
+        if (files[(size_t)w] < 0) { setup = false; break; }
+        unlink(path.c_str());
+        int sv[2];
+        if (socketpair(AF_UNIX, SOCK_STREAM, 0, sv) != 0) { setup = false; break; }
+        sock_parent[(size_t)w] = sv[0]; sock_child[(size_t)w] = sv[1];
+    }
+    std::atomic<int> *next = setup ? (std::atomic<int> *)mmap(nullptr, sizeof(std::atomic<int>), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0)
+                                   : (std::atomic<int> *)MAP_FAILED;
+    if (next == MAP_FAILED) {
+        for (int w = 0; w < procs; ++w)
+            for (int fd : {files[(size_t)w], sock_parent[(size_t)w], sock_child[(size_t)w]}) if (fd >= 0) close(fd);
+        cerr << "note: per-seed workers not available (" << strerror(errno) << "), running in-process\n";
+        return false;
+    }
     new (next) std::atomic<int>(0);
     out.flush();
     cerr.flush();
-    vector<pid_t> pids((size_t)procs);
-    vector<int> socks((size_t)procs), files((size_t)procs);
-    const char *tmpdir = getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp";
+    vector<pid_t> pids((size_t)procs, -1);
+    vector<int> socks = sock_parent;
     for (int w = 0; w < procs; ++w) {
-        int sv[2];
-        string path = string(tmpdir) + "/ribbit_gpu.XXXXXX";
-        files[(size_t)w] = mkstemp(&path[0]);
-        if (files[(size_t)w] < 0 || socketpair(AF_UNIX, SOCK_STREAM, 0, sv) != 0) { cerr << "ERROR: worker set-up: " << strerror(errno) << "\n"; exit(1); }
-        unlink(path.c_str());
         const pid_t pid = fork();
-        if (pid < 0) { cerr << "ERROR: fork: " << strerror(errno) << "\n"; exit(1); }
+        if (pid < 0) {  // fewer workers than planned: the parts are claimed dynamically, so the rest still gets done
+            cerr << "note: fork: " << strerror(errno) << " (" << w << " per-seed workers)\n";
+            for (int v = w; v < procs; ++v) { close(files[(size_t)v]); close(sock_parent[(size_t)v]); close(sock_child[(size_t)v]); }
+            procs = w;
+            break;
+        }
         if (pid == 0) {  // worker: never touches CUDA, never returns
-            close(sv[0]);
-            for (int v = 0; v < w; ++v) close(socks[(size_t)v]);
-            g_worker_fd = sv[1];
+            for (int v = 0; v < (int)socks.size(); ++v) { close(sock_parent[(size_t)v]); if (v != w) close(sock_child[(size_t)v]); }
+            g_worker_fd = sock_child[(size_t)w];
             for (int part = (*next)++; part < n_parts; part = (*next)++) {
                 std::ostringstream os;
                 body(part, os);
@@ -207,10 +225,10 @@ void forked_parts(int n_parts, int procs, ostream &out, Body body, Serve serve) 
             }
             _exit(0);
         }
-        close(sv[1]);
+        close(sock_child[(size_t)w]);
         pids[(size_t)w] = pid;
-        socks[(size_t)w] = sv[0];
     }
+    if (procs == 0) { munmap((void *)next, sizeof(std::atomic<int>)); return false; }
     // parent: serve GPU requests until every worker has closed its socket
     vector<pollfd> pf((size_t)procs);
     int open_socks = procs;
@@ -242,6 +260,7 @@ void forked_parts(int n_parts, int procs, ostream &out, Body body, Serve serve) 
     }
     for (const string &t : parts) out << t;
     munmap((void *)next, sizeof(std::atomic<int>));
+    return true;
 }
 
 #ifndef RIBBIT_HOST_MOTIF
@@ -492,6 +511,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     clock.mark("seed gate (K5) + motif rows (K7)");
     const int procs = host_procs();
     long served = 0;
+    bool in_workers = false;
 #ifndef RIBBIT_HOST_MOTIF
     if (procs > 1 && live.size() >= 4096) {
         // parts of roughly equal work (seed length + motif size as the weight), several per worker
@@ -503,7 +523,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
         for (int p = 1; p < n_parts; ++p)
             cut[(size_t)p] = (size_t)(std::lower_bound(acc.begin(), acc.end(), acc.back() * p / n_parts) - acc.begin());
         for (int p = 1; p <= n_parts; ++p) cut[(size_t)p] = std::max(cut[(size_t)p], cut[(size_t)p - 1]);
-        forked_parts(n_parts, procs, out,
+        const bool done = forked_parts(n_parts, procs, out,
                      [&](int part, ostream &o) { run_seeds(cut[(size_t)part], cut[(size_t)part + 1], o); },
                      [&](int fd) {
                          rb_seed sd;
@@ -513,6 +533,8 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
                          ++served;
                          return write_all(fd, &r, sizeof r);
                      });
+        in_workers = done;
+        if (!done) run_seeds(0, live.size(), out);
     } else
 #endif
         run_seeds(0, live.size(), out);
@@ -520,7 +542,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
 #ifndef RIBBIT_HOST_MOTIF
     if (getenv("RIBBIT_VERBOSE"))
         cerr << "K7 motif rows: " << g_motif.rows.size() << " in the batch, " << g_motif.misses + served << " single calls; per-seed stage on "
-             << ((procs > 1 && live.size() >= 4096) ? procs : 1) << " process(es)\n";
+             << (in_workers ? procs : 1) << " process(es)\n";
 #endif
     cerr << "Total number of seeds that are processed for alignment: " << processed_seeds << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
 }
