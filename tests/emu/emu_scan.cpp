@@ -3,6 +3,7 @@
 // kernel logic against the oracle where no GPU exists. It is not a product path: the product has no CPU fallback.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -82,6 +83,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
 
     std::vector<std::vector<Meta>> meta(lay.nbands, std::vector<Meta>((size_t)nw + 1, Meta{0u, 0u, 0u, 0u}));
     std::vector<ItemOut> items(chunks.size() * lay.nbands);
+    long tight_steps = 0;
 
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk ch = chunks[ci];
@@ -91,6 +93,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
             LaneState st[32];
             for (int j = 0; j < lay.bw; ++j) { cfg[j] = band_lane_cfg(lay, band, j); lane_cfg_set_contig(cfg[j], (int)L); }
             int H = warm0;
+            const bool tight = getenv("RB_EMU_NO_TIGHT") == nullptr;
             const int e0 = ch.w0;  // first emitting word
             int we = e0;           // word at which the lane state must be complete (end of the current warm-up)
             int force = 0;         // the warm-up rebuilds the reference machines: process its words bit-serially
@@ -161,6 +164,32 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                     if (it.emit_on) meta[band][w] = make_meta(sk.counts, sk.dmax[1], sk.dmax[2], it.slow, off);
                     prev_slow = slow;
                     ++w;
+                    // tight path of the kernel (whole-warp items): consecutive fast, emitting words with the sequential
+                    // phase-1 variant, running plane-word pointers and the fast-word test taken from the loaded words
+                    if (lay.bw == 32 && tight && w > we && w >= e0 && fastrun >= 4 && !prev_slow) {
+                        uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
+                        const int wend = std::min(std::min(ch.w1, nw - 1), (((int)L - lay.s_hi) >> 5) - 1);
+                        SeqPtrs sp[32];
+                        for (int j = 0; j < 32; ++j) { sp[j].o = cw + (w + 1); sp[j].b = cw + (w + 1 + (cfg[j].s >> 5) + 1); }
+                        const int w_in = w;
+                        while (w < wend) {
+                            if ((vprev & vcur) != 0xFFFFFFFFu) break;
+                            uint32_t vnext = 0, af[32 + 4] = {0};
+                            for (int j = 0; j < 32; ++j) af[j + 2] = lane_phase1_fast_seq(cfg[j], st[j], cw, w, (int)L, vnext, sp[j]);
+                            IterCtx it2; it2.w = w; it2.L = (int)L; it2.emit_on = 1; it2.slow = 0; it2.prev_slow = 0; it2.fastrun = 4;
+                            EmuSink sk2; sk2.out = &io; sk2.counts = 0u; sk2.dmax[0] = sk2.dmax[1] = sk2.dmax[2] = 0;
+                            const uint32_t off2 = (uint32_t)io.raw.size();
+                            for (int j = 0; j < 32; ++j)
+                                lane_phase2_fast(sk2, cfg[j], st[j], it2, j >= 2 ? af[j] : 0u, j >= 1 ? af[j + 1] : 0u,
+                                                 j + 1 < 32 ? af[j + 3] : 0u, j + 2 < 32 ? af[j + 4] : 0u);
+                            meta[band][w] = make_meta(sk2.counts, sk2.dmax[1], sk2.dmax[2], 0, off2);
+                            vprev = vcur; vcur = vnext;
+                            ++w;
+                            ++tight_steps;
+                        }
+                        if (w != w_in)
+                            for (int j = 0; j < 32; ++j) if (cfg[j].s) st[j].xc.idx = w + (cfg[j].s >> 5) + 1;
+                    }
                 }
                 if (replay) continue;
                 if (!restart) {
@@ -179,6 +208,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
         }
     }
 
+    if (getenv("RB_EMU_TRACE")) fprintf(stderr, "emu: %ld tight-loop steps\n", tight_steps);
     // merge (kernels M1-M3): buckets in word order; per bucket a pseudo record, then the records ranked by key
     std::vector<Rec> res[3];
     long long emax[2] = {0, 0};  // running maximum of elided_end_code (exclusive prefix), streams S and A
