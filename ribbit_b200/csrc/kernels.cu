@@ -336,10 +336,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
                 sp.o = cw + (w + 1);
                 sp.b = cw + (w + 1 + (cfg.s >> 5) + 1);
                 const int w_in = w;
+                const bool small_band = band_m0(b.lay, band) - 2 <= 15;  // uniform: the item holds shifts <= 15
                 while (w < wend) {
                     if ((vprev & vcur) != 0xFFFFFFFFu) break;
                     uint32_t vnext;  // v of word w + 1, from the plane word phase 1 loads anyway
-                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L, vnext, sp);
+                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L, vnext, sp, small_band);
                     uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
                     uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
                     IterCtx it;

@@ -586,7 +586,7 @@ RB_HD uint32_t lane_phase1(const LaneCfg& cfg, LaneState& st, const PlaneWord* c
 // lie in a run of at least 3 (anchor_size, parse_anchored_shiftxor.cpp:44). Everything else takes anchor_word.
 template <bool SEQ>
 RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t* v_next = nullptr,
-                                  SeqPtrs* sp = nullptr) {
+                                  SeqPtrs* sp = nullptr, bool small = true) {
     if (SEQ) {
         // every lane (idle ones too) reads the same word w+1: its v field is the caller's fast-word test for the next step
         const PlaneWord o = *sp->o, b = *sp->b;
@@ -614,9 +614,19 @@ RB_HD uint32_t lane_phase1_fast_t(const LaneCfg& cfg, LaneState& st, const Plane
     // runs that touch a word edge: their full length is known from the neighbours
     a &= (st.lenL + lead >= K2) ? ~lowmask(lead) : 0xFFFFFFFFu;
     a &= (trail + leadn >= K2) ? lowmask(32 - trail) : 0xFFFFFFFFu;
-    if (K2 <= 30) {  // small shifts: a run inside the word can be too long as well
+    if (small) {  // shifts <= 15 in this item: a run inside the word can be too long as well
+        // K2 ones in a row by doubling, branch-free for every lane: five steps reach min(K2, 32) ones, and 32 ones in a
+        // row cannot occur here (x is not all ones), so lanes with K2 > 30 end with e == 0
         uint32_t e = x;
-        for (int k = 1; k < K2;) { const int sh = (k < K2 - k) ? k : K2 - k; e &= e >> sh; k += sh; }
+        int k = 1;
+#pragma unroll
+        for (int step = 0; step < 5; ++step) {
+            int sh = K2 - k;
+            sh = sh < k ? sh : k;
+            sh = sh < 0 ? 0 : sh;
+            e &= e >> sh;
+            k += sh;
+        }
         if (e) {
             uint32_t d = e;
             for (int k = 1; k < K2;) { const int sh = (k < K2 - k) ? k : K2 - k; d |= d << sh; k += sh; }
@@ -646,8 +656,10 @@ RB_HD uint32_t lane_phase1_fast(const LaneCfg& cfg, LaneState& st, const PlaneWo
 }
 // the previous call (either phase-1 variant) was for word w-1
 // (tight loop; the caller owns the running pointers and restores st.xc.idx when it leaves the loop)
-RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t& v_next, SeqPtrs& sp) {
-    return lane_phase1_fast_t<true>(cfg, st, cw, w, L, &v_next, &sp);
+// small: some lane of the item has a shift <= 15 (uniform over the item; true is always correct)
+RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int w, int L, uint32_t& v_next, SeqPtrs& sp,
+                                    bool small) {
+    return lane_phase1_fast_t<true>(cfg, st, cw, w, L, &v_next, &sp, small);
 }
 
 // Phase 2 of a fast word (it.slow == 0, machines on) (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so

@@ -175,7 +175,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                         while (w < wend) {
                             if ((vprev & vcur) != 0xFFFFFFFFu) break;
                             uint32_t vnext = 0, af[32 + 4] = {0};
-                            for (int j = 0; j < 32; ++j) af[j + 2] = lane_phase1_fast_seq(cfg[j], st[j], cw, w, (int)L, vnext, sp[j]);
+                            for (int j = 0; j < 32; ++j) af[j + 2] = lane_phase1_fast_seq(cfg[j], st[j], cw, w, (int)L, vnext, sp[j], band_m0(lay, band) - 2 <= 15);
                             IterCtx it2; it2.w = w; it2.L = (int)L; it2.emit_on = 1; it2.slow = 0; it2.prev_slow = 0; it2.fastrun = 4;
                             EmuSink sk2; sk2.out = &io; sk2.counts = 0u; sk2.dmax[0] = sk2.dmax[1] = sk2.dmax[2] = 0;
                             const uint32_t off2 = (uint32_t)io.raw.size();
