@@ -9,33 +9,12 @@
 //   fasta_strip_kernel  per tile: sequence bytes staged in shared memory at their rank, then written out coalesced;
 //                       per header: its offset in the text and the number of sequence bytes in front of it
 // A control byte is '\n' (the next line is sequence until proven otherwise) or a '>' that follows a '\n' / starts the text.
+#include "fasta_core.h"
 #include "kernels.h"
 
 namespace rb {
 
 namespace {
-
-constexpr int FT_THREADS = 256;
-constexpr int FT_PER = 16;
-constexpr int FT_TILE = FT_THREADS * FT_PER;  // 4096 bytes
-
-enum : int { LT_SEQ = 0, LT_HDR = 1, LT_NONE = 2 };
-
-// 16 bytes of text as bit masks (bit i = byte i of the thread's slice): newlines, header starts ('>' behind a '\n'),
-// header bytes that follow a header start inside the slice, and the bytes in front of the slice's first control byte
-// (their line type comes from earlier slices). Byte-parallel: __vcmpeq4 + one multiply per word gathers the four
-// compare results into a nibble.
-struct Slice {
-    uint32_t w[4];     // the bytes
-    uint32_t valid;    // bytes inside the text
-    uint32_t nl, hs;   // control bytes
-    uint32_t hdr;      // bytes of header lines that start inside the slice (the '>' included, the '\n' not)
-    uint32_t before;   // valid bytes in front of the first control byte
-};
-
-__device__ __forceinline__ uint32_t eq_mask4(uint32_t word, uint32_t pattern) {
-    return ((__vcmpeq4(word, pattern) & 0x08040201u) * 0x01010101u) >> 24;  // bit k = byte k equals
-}
 
 __device__ __forceinline__ Slice load_slice(const uint8_t* __restrict__ text, long long nbytes, long long at) {
     Slice r;
@@ -53,32 +32,9 @@ __device__ __forceinline__ Slice load_slice(const uint8_t* __restrict__ text, lo
             r.w[k] = x;
         }
     }
-    r.valid = (1u << n) - 1u;
-    uint32_t nl = 0, gt = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        nl |= eq_mask4(r.w[k], 0x0A0A0A0Au) << (4 * k);
-        gt |= eq_mask4(r.w[k], 0x3E3E3E3Eu) << (4 * k);
-    }
     const uint32_t prev_nl = (at > 0 && at <= nbytes) ? (__ldg(text + at - 1) == '\n') : 1u;  // the text starts a line
-    r.nl = nl & r.valid;
-    r.hs = gt & ((r.nl << 1) | prev_nl) & r.valid;
-    // a header start at bit a and its newline at bit b > a: (X - hs) ^ X covers a..b (no other control byte lies between)
-    const uint32_t X = r.nl | 0x10000u;
-    r.hdr = ((X - r.hs) ^ X) & ~r.nl & 0xFFFFu;
-    const uint32_t ctrl = r.nl | r.hs;
-    r.before = (ctrl ? ((ctrl & (0u - ctrl)) - 1u) : 0xFFFFu) & r.valid;
+    slice_masks(r, n, prev_nl);
     return r;
-}
-
-__device__ __forceinline__ uint32_t slice_byte(const Slice& d, int i) { return (d.w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
-
-// The slice's last control byte as (index in tile) * 2 + line type it starts, -1 if none.
-__device__ __forceinline__ int last_control(const Slice& d, int first_index) {
-    const uint32_t ctrl = d.nl | d.hs;
-    if (!ctrl) return -1;
-    const int pos = 31 - __clz((int)ctrl);
-    return (first_index + pos) * 2 + (int)((d.hs >> pos) & 1u);
 }
 
 // inclusive max-scan over the block (values >= -1); returns the EXCLUSIVE result for this thread, *total = block max
@@ -142,7 +98,7 @@ __global__ void __launch_bounds__(FT_THREADS) fasta_tile_kernel(const uint8_t* _
     int tile_last;
     const int before = block_excl_max(last_control(d, threadIdx.x * FT_PER), s_warp, &tile_last);
     const int type = before < 0 ? LT_NONE : (before & 1);
-    const int n_before = __popc(d.before), n_after = __popc(d.valid & ~d.before & ~d.nl & ~d.hdr);
+    const int n_before = __popc(d.before), n_after = __popc(slice_seq_after(d));
     int pre = type == LT_NONE ? n_before : 0;
     int known = n_after + (type == LT_SEQ ? n_before : 0);
     int nh = __popc(d.hs);
@@ -213,7 +169,7 @@ __global__ void __launch_bounds__(FT_THREADS) fasta_strip_kernel(const uint8_t* 
     const int entry = (int)(ti.y >> 40);
     const int before = block_excl_max(last_control(d, threadIdx.x * FT_PER), s_warp, nullptr);
     const int type0 = before < 0 ? entry : (before & 1);
-    const uint32_t seq = (d.valid & ~d.before & ~d.nl & ~d.hdr) | (type0 == LT_SEQ ? d.before : 0u);
+    const uint32_t seq = slice_seq(d, type0);
     int tile_seq;
     const int rank = block_excl_sum(__popc(seq), s_warp, &tile_seq);
     const int hrank = block_excl_sum(__popc(d.hs), s_warp, nullptr);

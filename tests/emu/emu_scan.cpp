@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#include "fasta_core.h"
 #include "layout.h"
 #include "motif_core.h"
 #include "merge_core.h"
@@ -254,6 +255,76 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
 }
 
 void emu_free(void* p) { free(p); }
+
+// K0 on the CPU: the three passes of fasta_kernels.cu with the shared slice arithmetic (fasta_core.h), tiles and slices
+// walked in order. bases: capacity nbytes; hdr_pos / hdr_seq: capacity nbytes (one header needs at least one byte).
+// totals[0] = sequence bytes, totals[1] = headers.
+int emu_fasta(const uint8_t* text, int64_t nbytes, uint8_t* bases, int64_t* hdr_pos, int64_t* hdr_seq, int64_t* totals) {
+    const int64_t nt = (nbytes + FT_TILE - 1) / FT_TILE;
+    auto load = [&](int64_t at) {
+        Slice r;
+        const int n = (int)std::max<int64_t>(0, std::min<int64_t>(FT_PER, nbytes - at));
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = 0;
+            for (int j = 0; j < 4; ++j) if (4 * k + j < n) x |= (uint32_t)text[at + 4 * k + j] << (8 * j);
+            r.w[k] = x;
+        }
+        const uint32_t prev_nl = (at > 0 && at <= nbytes) ? (text[at - 1] == '\n') : 1u;
+        slice_masks(r, n, prev_nl);
+        return r;
+    };
+    struct Tile { int pre, known, nh, last; };
+    std::vector<Tile> tiles((size_t)nt);
+    for (int64_t t = 0; t < nt; ++t) {  // fasta_tile_kernel
+        Tile ti{0, 0, 0, LT_NONE};
+        int before = -1;
+        for (int th = 0; th < FT_THREADS; ++th) {
+            const Slice d = load(t * FT_TILE + (int64_t)th * FT_PER);
+            const int type = before < 0 ? LT_NONE : (before & 1);
+            const int nb = popc32(d.before), na = popc32(slice_seq_after(d));
+            ti.pre += type == LT_NONE ? nb : 0;
+            ti.known += na + (type == LT_SEQ ? nb : 0);
+            ti.nh += popc32(d.hs);
+            before = std::max(before, last_control(d, th * FT_PER));
+        }
+        ti.last = before < 0 ? LT_NONE : (before & 1);
+        tiles[(size_t)t] = ti;
+    }
+    std::vector<int64_t> seq_base((size_t)nt), hdr_base((size_t)nt);
+    std::vector<int> entry((size_t)nt);
+    int64_t seq = 0, hdr = 0;
+    int type = LT_SEQ;
+    for (int64_t t = 0; t < nt; ++t) {  // fasta_scan_kernel
+        const Tile& v = tiles[(size_t)t];
+        seq_base[(size_t)t] = seq; hdr_base[(size_t)t] = hdr; entry[(size_t)t] = type;
+        seq += (type == LT_SEQ ? v.pre : 0) + v.known;
+        hdr += v.nh;
+        if (v.last != LT_NONE) type = v.last;
+    }
+    totals[0] = seq; totals[1] = hdr;
+    for (int64_t t = 0; t < nt; ++t) {  // fasta_strip_kernel
+        int before = -1, rank = 0, hrank = 0;
+        for (int th = 0; th < FT_THREADS; ++th) {
+            const int64_t at = t * FT_TILE + (int64_t)th * FT_PER;
+            const Slice d = load(at);
+            const int type0 = before < 0 ? entry[(size_t)t] : (before & 1);
+            const uint32_t sq = slice_seq(d, type0);
+            int r = rank;
+            for (int i = 0; i < FT_PER; ++i)
+                if ((sq >> i) & 1u) bases[seq_base[(size_t)t] + r++] = (uint8_t)slice_byte(d, i);
+            for (uint32_t h = d.hs; h; h &= h - 1u) {
+                const int i = ctz32(h);
+                const int64_t k = hdr_base[(size_t)t] + hrank + popc32(d.hs & ((1u << i) - 1u));
+                hdr_pos[k] = at + i;
+                hdr_seq[k] = seq_base[(size_t)t] + rank + popc32(sq & ((1u << i) - 1u));
+            }
+            rank += popc32(sq);
+            hrank += popc32(d.hs);
+            before = std::max(before, last_control(d, th * FT_PER));
+        }
+    }
+    return 0;
+}
 
 // K7 on the CPU: the kernel's per-row scoring (motif_core.h) and its reduction rule (largest count, then smallest row; no
 // scoring row -> 0). seeds = n x {start, end, mlen}; out = n x {row, count}.

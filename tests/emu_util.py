@@ -18,6 +18,7 @@ def lib():
                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
                                   ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         _lib.emu_free.argtypes = [ctypes.c_void_p]
+        _lib.emu_fasta.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib.emu_motif_rows.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     return _lib
 
@@ -51,3 +52,15 @@ def emu_motif_rows(seq: bytes, seeds):
     out = np.zeros((len(sd), 2), np.int32)
     lib().emu_motif_rows(seq, len(seq), sd.ctypes.data, len(sd), out.ctypes.data)
     return out
+
+
+def emu_fasta(text: bytes):
+    """K0 on the CPU: (sequence bytes, header offsets in the text, sequence bytes in front of each header)."""
+    buf = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(1, np.uint8)
+    n = len(text)
+    bases = np.zeros(max(n, 1), np.uint8)
+    hpos = np.zeros(max(n, 1), np.int64)
+    hseq = np.zeros(max(n, 1), np.int64)
+    tot = np.zeros(2, np.int64)
+    lib().emu_fasta(buf.ctypes.data, n, bases.ctypes.data, hpos.ctypes.data, hseq.ctypes.data, tot.ctypes.data)
+    return bases[:tot[0]].tobytes(), hpos[:tot[1]].copy(), hseq[:tot[1]].copy()
