@@ -21,16 +21,19 @@ class ScanPipeline:
         self.pools = [ThreadPoolExecutor(max_workers=1) for _ in range(depth)]  # one host thread per context
         self.n = 0
 
-    def _run(self, k, buf, lengths):
+    def _run(self, k, buf, lengths, word_range):
         sc = self.scanners[k]
         sc.load_flat(buf, lengths)
+        if word_range is not None:
+            sc.set_word_range(*word_range)
         return sc.scan_compact(copy=self.copy) if self.compact else sc.scan(copy=self.copy)
 
-    def submit_flat(self, buf, lengths):
-        """buf: uint8 numpy array holding the contigs back to back (pinned for full-speed copies)."""
+    def submit_flat(self, buf, lengths, word_range=None):
+        """buf: uint8 numpy array holding the contigs back to back (pinned for full-speed copies). word_range: scan only
+        the words [first, last) of a single-contig batch (rb_set_word_range: one contig over several GPUs)."""
         k = self.n % self.depth
         self.n += 1
-        return self.pools[k].submit(self._run, k, buf, lengths)
+        return self.pools[k].submit(self._run, k, buf, lengths, word_range)
 
     def close(self):
         for p in self.pools:

@@ -23,6 +23,32 @@ def assign(lengths: Sequence[int], world: int) -> List[List[int]]:
     return [sorted(o) for o in owned]
 
 
+def plan_parts(lengths: Sequence[int], world: int, tol: float = 0.02, align_words: int = 1024) -> List[List[tuple]]:
+    """Strong-scaling partition by (contig, chunk): whole contigs by `assign`, then the most loaded rank
+    hands the tail of its largest part to the least loaded one until the loads (in 32-base words) differ by at most
+    tol x the mean. Returns, per rank, parts (contig, word_first, word_last) in (contig, word_first) order; a whole contig
+    is (i, 0, ceil(L/32)). Deterministic. A rank that owns a range of a contig scans it with rb_set_word_range."""
+    nw = [(int(L) + 31) // 32 for L in lengths]
+    parts: List[List[tuple]] = [[(i, 0, nw[i]) for i in o] for o in assign(lengths, world)]
+    if world > 1 and sum(nw) > 0:
+        mean = sum(nw) / world
+        for _ in range(8 * world):
+            load = [sum(b - a for _, a, b in p) for p in parts]
+            hi = max(range(world), key=lambda r: (load[r], -r))
+            lo = min(range(world), key=lambda r: (load[r], r))
+            diff = load[hi] - load[lo]
+            if diff <= tol * mean:
+                break
+            take = (diff // 2) // align_words * align_words
+            k = max(range(len(parts[hi])), key=lambda j: (parts[hi][j][2] - parts[hi][j][1], -j))
+            c, a, b = parts[hi][k]
+            if take <= 0 or b - a <= take:
+                break
+            parts[hi][k] = (c, a, b - take)
+            parts[lo].append((c, b - take, b))
+    return [sorted(p) for p in parts]
+
+
 def scan_local(contigs: Sequence[bytes], mine: Sequence[int], scan_fn: Callable[[List[bytes]], List[dict]]) -> Dict[int, dict]:
     """Scans the contigs this rank owns as one batch. scan_fn(list of contig bytes) -> list of per-contig results."""
     res = scan_fn([contigs[i] for i in mine]) if mine else []
