@@ -48,7 +48,7 @@ struct rb_ctx {
     const void* ascii_dev_ext = nullptr;
 
     DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
-        d_meta, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys, d_text, d_ftiles, d_finfo, d_ftot, d_hpos, d_hseq;
+        d_meta, d_bsum, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys, d_text, d_ftiles, d_finfo, d_ftot, d_hpos, d_hseq;
     DevBatch batch{};
 
     // pinned host results
@@ -117,10 +117,11 @@ int ensure_pinned(rb_ctx* c, void*& p, size_t& cap, size_t bytes) {
     return RB_OK;
 }
 
-// records per word reserved for one (chunk, band) item; an item that needs more triggers an exact re-run
+// raw slots per word reserved for one (chunk, band) item (a fast word needs one slot per motif size and stream with
+// candidates, a slow word one per candidate); an item that needs more triggers an exact re-run
 int records_per_word(const BandLayout& lay, int band) {
     const int m0 = band_m0(lay, band);
-    return m0 <= 12 ? 12 : 6;
+    return m0 <= 12 ? 8 : 4;
 }
 
 // Cuts the contigs' words into chunks. range_last >= 0: single-contig batch, only words [range_first, range_last).
@@ -149,6 +150,7 @@ int build_geometry(rb_ctx* c, const int64_t* offsets, const int32_t* lengths, in
     long long pw = 0, nb = 0, total_words = 0;
     for (int i = 0; i < n; ++i) {
         if (lengths[i] < 0 || (long long)lengths[i] > 0x7FFFFFFFll - 4096) return fail(c, RB_E_RANGE, "contig %d: length %d out of range", i, lengths[i]);
+        if (offsets[i] < 0) return fail(c, RB_E_ARG, "contig %d: negative offset", i);
         Contig cg;
         cg.L = lengths[i];
         cg.nw = (int32_t)(((long long)lengths[i] + 31) / 32);
@@ -231,6 +233,7 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.n_merge_blocks = (int)((b.n_buckets + MERGE_BLOCK - 1) / MERGE_BLOCK);
     if ((rc = ensure(c, c->d_planes, (size_t)b.n_plane_words * sizeof(PlaneWord)))) return rc;
     if ((rc = ensure(c, c->d_meta, (size_t)b.n_buckets * c->lay.nbands * sizeof(Meta)))) return rc;
+    if ((rc = ensure(c, c->d_bsum, (size_t)std::max<long long>(b.n_buckets, 1) * sizeof(BucketSum)))) return rc;
     if ((rc = ensure(c, c->d_counters, 4 * sizeof(int)))) return rc;
     if ((rc = ensure(c, c->d_partial, ((size_t)b.n_merge_blocks + 1) * sizeof(BlockPartial)))) return rc;
     if ((rc = ensure(c, c->d_contig_off, 3 * ((size_t)n + 1) * sizeof(long long)))) return rc;
@@ -242,6 +245,7 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.planes = (PlaneWord*)c->d_planes.p;
     b.chunks = (const Chunk*)c->d_chunks.p;
     b.meta = (Meta*)c->d_meta.p;
+    b.bsum = (BucketSum*)c->d_bsum.p;
     b.counters = (int*)c->d_counters.p;
     b.partial = (BlockPartial*)c->d_partial.p;
     b.contig_off = (long long*)c->d_contig_off.p;
@@ -293,7 +297,7 @@ void rb_destroy(rb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_chunks,
-                      &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_raw, &c->d_counters,
+                      &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_bsum, &c->d_raw, &c->d_counters,
                       &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long, &c->d_mitems, &c->d_mkeys,
                       &c->d_text, &c->d_ftiles, &c->d_finfo, &c->d_ftot, &c->d_hpos, &c->d_hseq};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -449,6 +453,16 @@ int rb_scan_device(rb_ctx* c) {
     DevBatch& b = c->batch;
     rb_timing tm{};
     cudaStream_t st = c->stream;
+    // the final pool is sized before the step from the input size (or the previous result), so that the whole step is
+    // enqueued without a host round trip; if it turns out too small only the last kernel runs again
+    long long bases = 0;
+    for (const Contig& cg : c->contigs) bases += cg.L;
+    if (b.gb_first > 0 || b.n_active < b.n_buckets) bases = 32ll * b.n_active;
+    long long want = std::max<long long>(1024 + bases / 4, c->scanned ? (c->totals[0] + c->totals[1] + c->totals[2]) * 9 / 8 : 0);
+    int rc = ensure(c, c->d_dst, (size_t)want * sizeof(Rec));
+    if (rc) return rc;
+    b.dst = (Rec*)c->d_dst.p;
+    b.dst_cap = (long long)(c->d_dst.cap / sizeof(Rec));
     RB_CUDA(c, cudaEventRecord(c->ev[0], st));
     launch_pack(b, st);
     tm.launches += b.n_plane_words ? 1 : 0;
@@ -459,35 +473,41 @@ int rb_scan_device(rb_ctx* c) {
         tm.launches += b.n_items ? 1 : 0;
         if (attempt == 0) RB_CUDA(c, cudaEventRecord(c->ev[2], st));
         launch_merge_count(b, st);
-        tm.launches += b.n_buckets ? 2 : 0;
-        // stream sizes and the overflow flag are needed on the host to size the final pool
+        launch_merge_write(b, st);
+        tm.launches += b.n_buckets ? 3 : 0;
+        RB_CUDA(c, cudaEventRecord(c->ev[3], st));
         RB_CUDA(c, cudaMemcpyAsync(c->h_small, b.totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        RB_CUDA(c, cudaMemcpyAsync(c->h_small + 4, b.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(c, cudaMemcpyAsync(c->h_small + 4, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         RB_CUDA(c, cudaStreamSynchronize(st));
         RB_CUDA(c, cudaGetLastError());
         const int* counters = (const int*)(c->h_small + 4);
         if (b.n_buckets == 0) { c->h_small[0] = c->h_small[1] = c->h_small[2] = 0; }
         tm.restarts += counters[1];
+        if (b.n_items && counters[2]) return fail(c, RB_E_RANGE, "rb_scan_device: more candidates in one 32-base word than the bucket counters hold");
         if (b.n_items == 0 || counters[0] == 0) break;
         if (attempt >= 2) return fail(c, RB_E_CUDA, "rb_scan_device: candidate buffers still too small after an exact re-run");
-        // some item produced more records than reserved: size every item from the counts and run again
+        // some item produced more slots than reserved: size every item from the counts and run again
         std::vector<int> counts(c->item_base.size());
         RB_CUDA(c, cudaMemcpy(counts.data(), b.item_count, counts.size() * sizeof(int), cudaMemcpyDeviceToHost));
         size_items(c, &counts);
-        int rc = upload_items(c);
+        rc = upload_items(c);
         if (rc) return rc;
         ++tm.retries;
     }
     for (int s = 0; s < 3; ++s) c->totals[s] = c->h_small[s];
     const long long total = c->totals[0] + c->totals[1] + c->totals[2];
-    int rc = ensure(c, c->d_dst, (size_t)std::max<long long>(total, 1) * sizeof(Rec));
-    if (rc) return rc;
-    b.dst = (Rec*)c->d_dst.p;
-    launch_merge_write(b, st);
-    tm.launches += b.n_buckets ? 1 : 0;
-    RB_CUDA(c, cudaEventRecord(c->ev[3], st));
-    RB_CUDA(c, cudaStreamSynchronize(st));
-    RB_CUDA(c, cudaGetLastError());
+    if (total > b.dst_cap) {  // the estimate was too small: the last kernel once more into a pool of the exact size
+        rc = ensure(c, c->d_dst, (size_t)total * sizeof(Rec));
+        if (rc) return rc;
+        b.dst = (Rec*)c->d_dst.p;
+        b.dst_cap = (long long)(c->d_dst.cap / sizeof(Rec));
+        launch_merge_write(b, st);
+        tm.launches += 1;
+        ++tm.retries;
+        RB_CUDA(c, cudaEventRecord(c->ev[3], st));
+        RB_CUDA(c, cudaStreamSynchronize(st));
+        RB_CUDA(c, cudaGetLastError());
+    }
     RB_CUDA(c, cudaEventElapsedTime(&tm.pack_ms, c->ev[0], c->ev[1]));
     RB_CUDA(c, cudaEventElapsedTime(&tm.scan_ms, c->ev[1], c->ev[2]));
     RB_CUDA(c, cudaEventElapsedTime(&tm.merge_ms, c->ev[2], c->ev[3]));
@@ -600,6 +620,7 @@ int rb_get_planes(rb_ctx* c, int32_t contig, uint32_t* hi, uint32_t* lo, uint32_
     if (!c) return RB_E_ARG;
     if (!c->scanned) return fail(c, RB_E_STATE, "rb_get_planes: planes exist after rb_scan_device");
     if (contig < 0 || contig >= c->batch.n_contigs) return fail(c, RB_E_ARG, "rb_get_planes: contig out of range");
+    RB_CUDA(c, cudaSetDevice(c->device));
     const Contig& cg = c->contigs[contig];
     std::vector<PlaneWord> tmp((size_t)cg.nw);
     if (cg.nw) RB_CUDA(c, cudaMemcpy(tmp.data(), (const PlaneWord*)c->d_planes.p + cg.word_base, tmp.size() * sizeof(PlaneWord), cudaMemcpyDeviceToHost));

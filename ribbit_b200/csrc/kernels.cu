@@ -5,6 +5,7 @@
 //   K6 merge kernels   ordered compaction of the candidate buckets        call order of addSeedToSeedPositions*
 // The per-lane logic lives in scan_core.h / merge_core.h, which the CPU warp emulator of tests/ compiles too.
 #include "kernels.h"
+#include "scan_tight.h"
 
 namespace rb {
 
@@ -93,19 +94,20 @@ struct GpuSink {
     Rec* base;
     int cap;
     int* cnt;
-    uint32_t counts;  // nP | nS << 10 | nA << 20 of this lane in this bucket
+    int nslots;  // slots this lane wrote into this bucket
     int dS, dA;
-    __device__ __forceinline__ void rec(int stream, int start, int end, int mlen, int flags, int key) {
+    __device__ __forceinline__ void put(const Rec& r) {
         const int idx = atomicAdd(cnt, 1);
-        if (idx < cap) {
-            int4 v;
-            v.x = start; v.y = end; v.z = mlen | (flags << 16) | (stream << REC_STREAM_SHIFT); v.w = key;
-            *reinterpret_cast<int4*>(base + idx) = v;
-        }
-        counts += 1u << (10 * stream);
+        if (idx < cap) *reinterpret_cast<int4*>(base + idx) = make_int4(r.start, r.end, r.mflags, r.key);
+        ++nslots;
     }
-    __device__ __forceinline__ void dropped(int stream, int tw) {
-        if (stream == STREAM_S) dS = max(dS, tw + 1); else dA = max(dA, tw + 1);
+    __device__ __forceinline__ void rec(int stream, int start, int end, int mlen, int flags, int key) {
+        Rec r;
+        r.start = start; r.end = end; r.mflags = mlen | (flags << 16) | (stream << REC_STREAM_SHIFT); r.key = key;
+        put(r);
+    }
+    __device__ __forceinline__ void entry(int stream, int mlen, uint32_t mask, uint32_t smask, int last) {
+        put(make_entry(stream, mlen, mask, smask, last));
     }
     __device__ __forceinline__ void dropped_mask(int stream, uint32_t el) {
         const int d = 32 - __clz((int)el);  // 0 when nothing was elided
@@ -117,15 +119,117 @@ static const int SCAN_WARPS = 1;
 
 // fast -> slow transition (scan_core.h, lane_to_slow) out of line and with scalar arguments, so that the rare call does
 // not weigh on the register allocation of the scan loop
-__device__ __noinline__ bool slow_entry(uint32_t Ps, uint32_t r8s, uint32_t Pa, uint32_t r8a, uint32_t x_prev, int lastRS, int w,
-                                        SlowEntry& e) {
+__device__ __noinline__ bool slow_entry(uint32_t Ps, uint32_t r8s, uint32_t Pa, uint32_t r8a, uint32_t x_prev, const PlaneWord* cw, int w,
+                                        int s, SlowEntry& e) {
     EvCarry cs, ca;
     cs.P = Ps; cs.r8 = r8s; ca.P = Pa; ca.r8 = r8a;
     SlowEntry t;
     if (!win_from_fast(cs, 32 * (w - 1), t.S) || !win_from_fast(ca, 32 * (w - 1), t.A)) return false;
-    t.pst = (x_prev >> 31) ? lastRS : -1;
+    t.pst = (x_prev >> 31) ? perfect_run_start(cw, w - 1, 32, s, x_prev) : -1;
     e = t;
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The tight loop (scan_tight.h): consecutive fast, emitting words of the item(s) of a warp. Out of line: it has its own
+// register allocation, the general path's state waits in local memory meanwhile.
+// ---------------------------------------------------------------------------------------------------------------
+struct TightIO {
+    TightState t;
+    TightCfg c;
+    const PlaneWord* cw;
+    Meta* meta;        // bucket metadata of the item's (band, contig)
+    Rec* raw;          // raw pool
+    uint32_t off;      // raw-pool index of the next slot of the item
+    uint32_t cap_end;  // first index past the item's reservation
+    int w, wend, L;
+    int on;            // the group takes part (0: finished or warming up; its lanes only keep the warp converged)
+};
+
+template <int BW, bool SMALL>
+__device__ __noinline__ void tight_run(TightIO* io) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int g = lane / BW, j = lane % BW;
+    const unsigned gmask = (BW == 32) ? FULL : (((1u << BW) - 1u) << (g * BW));
+    const unsigned lt = (1u << lane) - 1u;
+    TightState t = io->t;
+    const TightCfg c = io->c;
+    const PlaneWord* __restrict__ cw = io->cw;
+    Rec* __restrict__ raw = io->raw;
+    uint32_t off = io->off;
+    const uint32_t cap_end = io->cap_end;
+    int w = io->w;
+    const int wend = io->wend, L = io->L;
+    const bool on = io->on != 0;
+    const uint4* po = reinterpret_cast<const uint4*>(cw + (w + 1));
+    const uint2* pb = reinterpret_cast<const uint2*>(cw + (w + 1 + (c.s >> 5) + 1));
+    Meta* mp = io->meta + w;
+    uint32_t vprev = on ? cw[w - 1].v : FULL, vcur = on ? cw[w].v : FULL;
+    bool susp = true, susc = true;  // !SMALL: nothing is known about the two words in front: the first steps take the exact anchors
+    int zc = 0;                     // consecutive words without a passing substitution window in any lane (saturating)
+    for (;;) {
+        // every group that takes part must have a fast word in front of it, else the warp leaves the loop
+        const bool go = !on || (w < wend && (vprev & vcur) == FULL);
+        if (!__all_sync(FULL, go) || !__any_sync(FULL, on)) break;
+        const uint4 o = __ldg(po);
+        const uint2 bb = __ldg(pb);
+        ++po; pb += 2;
+        uint32_t xn, l1;
+        bool sus;
+        const int lenL0 = t.lenL;
+        uint32_t a = tight_phaseA<SMALL>(c, t, o.x, o.y, bb.x, bb.y, xn, l1, sus);
+        bool rare = __any_sync(FULL, sus);
+        if (!SMALL) {
+            const bool r3 = rare | susc | susp;
+            susp = susc; susc = rare; rare = r3;
+        }
+        if (rare) a = tight_anchor_exact<SMALL>(c, t, cw, w, L, xn, lenL0);
+        const uint32_t pair = a | __shfl_down_sync(FULL, a, 1);
+        const uint32_t an = __shfl_up_sync(FULL, pair, 2) | __shfl_down_sync(FULL, pair, 1);
+        uint32_t passS, passA, cand;
+        tight_windows(c, t, an, l1, passS, passA, cand);
+        const int p0 = 32 * w;
+        TightOut oa, os;
+        tight_events_A<SMALL>(c, t, p0, passA, oa);
+        const bool actS = __any_sync(FULL, passS != 0u);
+        os.x = 0u; os.s = 0u; os.el = 0u; os.last = 0;
+        if (actS || zc < 2) {
+            tight_events_S(t, p0, passS, os);
+            zc = actS ? 0 : zc + 1;
+        }
+        cand &= c.mmask;
+        // mask entries: one slot per (lane, stream) with surviving candidates, packed by ballot
+        const uint32_t off_in = off;
+        const bool hA = on && oa.x != 0u;
+        const unsigned balA = __ballot_sync(FULL, hA);
+        if (balA) {
+            const unsigned mine = balA & gmask;
+            const uint32_t pos = off + __popc(mine & lt);
+            if (hA && pos < cap_end) *reinterpret_cast<int4*>(raw + pos) = make_int4((int)oa.x, (int)oa.s, c.s | (REC_ENTRY << 16) | (STREAM_A << REC_STREAM_SHIFT), oa.last);
+            off += __popc(mine);
+        }
+        const bool hS = on && os.x != 0u, hP = on && cand != 0u;
+        if (__any_sync(FULL, hS | hP)) {
+            const unsigned mS = __ballot_sync(FULL, hS) & gmask, mP = __ballot_sync(FULL, hP) & gmask;
+            const uint32_t posS = off + __popc(mS & lt);
+            if (hS && posS < cap_end) *reinterpret_cast<int4*>(raw + posS) = make_int4((int)os.x, (int)os.s, c.s | (REC_ENTRY << 16) | (STREAM_S << REC_STREAM_SHIFT), os.last);
+            off += __popc(mS);
+            const uint32_t posP = off + __popc(mP & lt);
+            if (hP && posP < cap_end) *reinterpret_cast<int4*>(raw + posP) = make_int4((int)cand, (int)(t.xc & ~l1), c.s | (REC_ENTRY << 16) | (STREAM_P << REC_STREAM_SHIFT), 0);
+            off += __popc(mP);
+        }
+        const uint32_t elA = __reduce_or_sync(gmask, oa.el), elS = __reduce_or_sync(gmask, os.el);
+        if (j == 0 && on) *mp = make_meta((int)(off - off_in), 32 - __clz((int)elS), 32 - __clz((int)elA), 0, off_in);
+        ++mp;
+        tight_rotate(t, xn);
+        vprev = vcur; vcur = o.w;
+        ++w;
+    }
+    if (!SMALL && c.s && on) t.lenL = tight_lenL_lookup(c, t, cw, w);  // the general path carries the run length
+    io->t = t;
+    io->off = off;
+    io->w = w;
 }
 
 template <int BW>
@@ -186,7 +290,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             if (bits != gmask) alln = false;
         }
         if (alln) {
-            for (int wq = ch.w0 + j; wq < ch.w1; wq += BW) meta[wq] = make_meta(0u, 0, 0, 1, off0);
+            for (int wq = ch.w0 + j; wq < ch.w1; wq += BW) meta[wq] = make_meta(0, 0, 0, 1, off0);
             if (j == 0) b.item_count[item] = 0;
             active = false;
         }
@@ -202,30 +306,32 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     lane_init(cfg, st, cw, q);
     int w = q;
     int prev_slow = 1, fastrun = 0;
-    uint32_t off = off0;  // raw-pool index of the next bucket's first record
+    uint32_t off = off0;  // raw-pool index of the next bucket's first slot
     if (j == 0) *cnt = 0;
     __syncwarp();
     int restarts = 0;
     if (active && ch.w0 >= ch.w1) {  // empty contig: only the tail bucket
         active = false;
         if (ch.last) {
-            if (j == 0) meta[ch.w1] = make_meta(0u, 0, 0, 1, off0);
+            if (j == 0) meta[ch.w1] = make_meta(0, 0, 0, 1, off0);
         }
         if (j == 0) b.item_count[item] = 0;
     }
 
     const int guard = b.lay.guard;
+    const bool small_band = band_m0(b.lay, band) - 2 <= 15;  // the item holds shifts <= 15 (uniform over the warp: see launch_scan)
     // The neighbour anchors of lanes at the edge of an item need no masking: lanes 0 and 1 of an item are halo
     // shifts (never motif lanes) and a motif lane has j + 2 <= mpb + 3 < BW (layout.h), so every value a motif lane
     // reads comes from its own item.
     for (;;) {
-        // ---- end of the chunk: tail flush (last chunk of a contig), record count -------------------------------
+        // ---- end of the chunk: tail flush (last chunk of a contig), slot count ---------------------------------
         if (active && w >= ch.w1) {
             if (ch.last) {
-                sk.counts = 0u;
+                sk.nslots = 0;
                 lane_tail(sk, cfg, st, L);
-                const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
-                if (j == 0) meta[ch.w1] = make_meta(counts, 0, 0, 1, off);
+                const int ns = __reduce_add_sync(gmask, sk.nslots);
+                if (j == 0) meta[ch.w1] = make_meta(min(ns, META_MAX_SLOTS), 0, 0, 1, off);
+                if (ns > META_MAX_SLOTS && j == 0) atomicAdd(b.counters + 2, 1);
             }
             __syncwarp(gmask);
             if (j == 0) {
@@ -270,7 +376,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             SlowEntry se;
             se.S = st.S; se.A = st.A; se.pst = st.pst;
             bool conv_ok = !trans || w >= q + Ha;  // the machines run in this word (not an anchors-only warm-up word)
-            if (trans && conv_ok && cfg.motif) conv_ok = slow_entry(st.es.P, st.es.r8, st.ea.P, st.ea.r8, st.x_prev, st.lastRS, w, se);
+            if (trans && conv_ok && cfg.motif) conv_ok = slow_entry(st.es.P, st.es.r8, st.ea.P, st.ea.r8, st.x_prev, cw, w, cfg.s, se);
             const unsigned conv_fail = __ballot_sync(0xFFFFFFFFu, !conv_ok) & gmask;
             if (trans) {
                 if (!conv_fail) {
@@ -312,51 +418,41 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
         } else if (active) {
             IterCtx it;
             it.w = w; it.L = L; it.emit_on = w >= we && w >= e0; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
-            sk.counts = 0u; sk.dS = 0; sk.dA = 0;
+            sk.nslots = 0; sk.dS = 0; sk.dA = 0;
             lane_phase2(sk, cfg, st, cw, it, a_m2, a_m1, a_p1, a_p2, w >= q + Ha);
             if (it.emit_on) {
-                const uint32_t counts = __reduce_add_sync(gmask, sk.counts);
+                const int ns = __reduce_add_sync(gmask, sk.nslots);
                 const int dS = __reduce_max_sync(gmask, sk.dS), dA = __reduce_max_sync(gmask, sk.dA);
-                if (j == 0) meta[w] = make_meta(counts, dS, dA, it.slow, off);
-                off += (counts & 0x3FFu) + ((counts >> 10) & 0x3FFu) + (counts >> 20);
+                if (j == 0) meta[w] = make_meta(min(ns, META_MAX_SLOTS), dS, dA, it.slow, off);
+                if (ns > META_MAX_SLOTS && j == 0) atomicAdd(b.counters + 2, 1);
+                off += (uint32_t)ns;
             }
             prev_slow = slow;
             ++w;
         }
 
-        // ---- tight path: consecutive fast, emitting words of a whole-warp item ---------------------------------
-        if constexpr (BW == 32) {
-            // word `we` (state check) and the first fast words of a stretch (keep filter not yet trusted) go through the
-            // general path; the tight loop stops before the contig's tail zone (anchor view differs from X_s there)
-            if (active && !badmask && w > we && w >= e0 && fastrun >= 4 && !prev_slow && !(b.debug & 1)) {
-                uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
-                const int wend = min(min(ch.w1, cg.nw - 1), ((L - b.lay.s_hi) >> 5) - 1);
-                Meta* mp = meta + w;
-                SeqPtrs sp;
-                sp.o = cw + (w + 1);
-                sp.b = cw + (w + 1 + (cfg.s >> 5) + 1);
-                const int w_in = w;
-                const bool small_band = band_m0(b.lay, band) - 2 <= 15;  // uniform: the item holds shifts <= 15
-                while (w < wend) {
-                    if ((vprev & vcur) != 0xFFFFFFFFu) break;
-                    uint32_t vnext;  // v of word w + 1, from the plane word phase 1 loads anyway
-                    const uint32_t af = lane_phase1_fast_seq(cfg, st, cw, w, L, vnext, sp, small_band);
-                    uint32_t f_m2 = __shfl_up_sync(0xFFFFFFFFu, af, 2), f_m1 = __shfl_up_sync(0xFFFFFFFFu, af, 1);
-                    uint32_t f_p1 = __shfl_down_sync(0xFFFFFFFFu, af, 1), f_p2 = __shfl_down_sync(0xFFFFFFFFu, af, 2);
-                    IterCtx it;
-                    it.w = w; it.L = L; it.emit_on = 1; it.slow = 0; it.prev_slow = 0; it.fastrun = 4;
-                    sk.counts = 0u; sk.dS = 0; sk.dA = 0;
-                    lane_phase2_fast(sk, cfg, st, it, f_m2, f_m1, f_p1, f_p2);
-                    const uint32_t counts = __reduce_add_sync(0xFFFFFFFFu, sk.counts);
-                    const int dS = __reduce_max_sync(0xFFFFFFFFu, sk.dS), dA = __reduce_max_sync(0xFFFFFFFFu, sk.dA);
-                    if (j == 0) *mp = make_meta(counts, dS, dA, 0, off);
-                    ++mp;
-                    off += (counts & 0x3FFu) + ((counts >> 10) & 0x3FFu) + (counts >> 20);
-                    vprev = vcur; vcur = vnext;
-                    ++w;
-                }
-                if (w != w_in && cfg.s) st.xc.idx = w + (cfg.s >> 5) + 1;  // the cached plane word: the last b operand
+        // ---- tight path: consecutive fast, emitting words ------------------------------------------------------------
+        // word `we` (state check) and the first fast words of a stretch (keep filter not yet trusted) go through the
+        // general path; the tight loop stops before the contig's tail zone (the anchor view differs from X_s there)
+        const bool tight_ok = active && !badmask && w > we && w >= e0 && fastrun >= 4 && !prev_slow && !(b.debug & 1);
+        const int wend = min(min(ch.w1, cg.nw - 1), ((L - b.lay.s_hi) >> 5) - 1);
+        const bool want = tight_ok && w < wend && (cw[w - 1].v & cw[w].v) == 0xFFFFFFFFu;
+        // every group with work must be able to enter, else the warp keeps to the general path for this word
+        if (__any_sync(0xFFFFFFFFu, want) && __all_sync(0xFFFFFFFFu, want || !active)) {
+            TightIO io;
+            tight_enter(cfg, st, io.t);
+            io.c = make_tight_cfg(cfg);
+            io.cw = cw; io.meta = meta; io.raw = b.raw; io.off = off; io.cap_end = off0 + (uint32_t)sk.cap;
+            io.w = w; io.wend = wend; io.L = L; io.on = want ? 1 : 0;
+            if (small_band) tight_run<BW, true>(&io); else tight_run<BW, false>(&io);
+            if (want) {
+                tight_leave(io.t, st);
+                if (io.w != w && cfg.s) st.xc.idx = io.w + (cfg.s >> 5) + 1;  // the cached plane word: the last b operand
+                w = io.w;
+                off = io.off;
+                if (j == 0) *cnt = (int)(off - off0);
             }
+            __syncwarp();
         }
     }
 }
@@ -384,19 +480,10 @@ struct BucketInfo {
     unsigned long long emax[2];     // contig << 32 | elided_end_code
 };
 
-__device__ __forceinline__ BucketInfo bucket_info(const DevBatch& b, long long gb) {
+__device__ __forceinline__ BucketInfo bucket_info_from(const DevBatch& b, long long gb, const unsigned (&tot)[3], int slow, int dS, int dA) {
     BucketInfo bi;
     bi.c = find_segment(b.bucket_base, b.n_contigs, gb);
     bi.w = (int)(gb - b.bucket_base[bi.c]);
-    unsigned tot[3] = {0u, 0u, 0u};
-    int slow = 0, dS = 0, dA = 0;
-    for (int k = 0; k < b.lay.nbands; ++k) {
-        const Meta m = b.meta[(long long)k * b.n_buckets + gb];
-        tot[0] += meta_cnt(m, 0); tot[1] += meta_cnt(m, 1); tot[2] += meta_cnt(m, 2);
-        slow |= meta_slow(m);
-        dS = max(dS, meta_dmax(m, STREAM_S));
-        dA = max(dA, meta_dmax(m, STREAM_A));
-    }
     for (int s = 0; s < 3; ++s) {
         bi.pseudo[s] = bucket_has_pseudo(s, slow, (int)tot[s]) ? 1u : 0u;
         bi.n[s] = tot[s] + bi.pseudo[s];
@@ -405,6 +492,12 @@ __device__ __forceinline__ BucketInfo bucket_info(const DevBatch& b, long long g
     bi.emax[0] = eS ? (((unsigned long long)bi.c << 32) | eS) : 0ull;
     bi.emax[1] = eA ? (((unsigned long long)bi.c << 32) | eA) : 0ull;
     return bi;
+}
+// from the per-bucket summary merge_count_kernel left behind
+__device__ __forceinline__ BucketInfo bucket_info(const DevBatch& b, long long gb) {
+    const BucketSum bs = b.bsum[gb];
+    const unsigned tot[3] = {bs.n[0], bs.n[1], bs.n[2]};
+    return bucket_info_from(b, gb, tot, bs.dS >> 7, bs.dS & 0x3F, bs.dA & 0x3F);
 }
 
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
@@ -445,12 +538,49 @@ __device__ __forceinline__ void block_scan(const unsigned (&n)[3], const unsigne
     }
 }
 
+// thread = bucket: expands the mask entries of the bucket far enough to know which candidates reach the consumer's cutoff
+// (the kept mask replaces the entry's E mask in the raw pool), counts the bucket's records per stream, leaves the bucket
+// summary for merge_write_kernel and the block sums for the prefix.
 __global__ void __launch_bounds__(MERGE_BLOCK) merge_count_kernel(DevBatch b) {
     const long long gb = b.gb_first + (long long)blockIdx.x * MERGE_BLOCK + threadIdx.x;
     unsigned n[3] = {0u, 0u, 0u};
     unsigned long long e[2] = {0ull, 0ull};
     if (gb < b.gb_first + b.n_active) {
-        const BucketInfo bi = bucket_info(b, gb);
+        const int c = find_segment(b.bucket_base, b.n_contigs, gb);
+        const int w = (int)(gb - b.bucket_base[c]);
+        const PlaneWord* __restrict__ cw = b.planes + b.contigs[c].word_base;
+        unsigned tot[3] = {0u, 0u, 0u};
+        int slow = 0, dS = 0, dA = 0;
+        for (int k = 0; k < b.lay.nbands; ++k) {
+            const Meta m = b.meta[(long long)k * b.n_buckets + gb];
+            const int ns = meta_slots(m);
+            slow |= meta_slow(m);
+            dS = max(dS, meta_dmax(m, STREAM_S));
+            dA = max(dA, meta_dmax(m, STREAM_A));
+            for (int i = 0; i < ns; ++i) {
+                Rec* rp = b.raw + m.off + i;
+                const int4 v = *reinterpret_cast<const int4*>(rp);
+                Rec r;
+                r.start = v.x; r.end = v.y; r.mflags = v.z; r.key = v.w;
+                const int st = rec_stream(r);
+                if (rec_is_entry(r)) {
+                    int el;
+                    const uint32_t kept = entry_kept_mask(r, w, cw, el);
+                    if (kept != (uint32_t)r.start) rp->start = (int)kept;
+                    tot[st] += (unsigned)__popc(kept);
+                    if (st == STREAM_S) dS = max(dS, el);
+                    if (st == STREAM_A) dA = max(dA, el);
+                } else {
+                    tot[st] += 1u;
+                }
+            }
+        }
+        BucketSum bs;
+        for (int s = 0; s < 3; ++s) bs.n[s] = (unsigned short)min(tot[s], 0xFFFFu);
+        if (tot[0] > 0xFFFFu || tot[1] > 0xFFFFu || tot[2] > 0xFFFFu) atomicAdd(b.counters + 2, 1);
+        bs.dS = (unsigned char)(dS | (slow << 7)); bs.dA = (unsigned char)dA;
+        b.bsum[gb] = bs;
+        const BucketInfo bi = bucket_info_from(b, gb, tot, slow, dS, dA);
         for (int s = 0; s < 3; ++s) n[s] = bi.n[s];
         e[0] = bi.emax[0]; e[1] = bi.emax[1];
     }
@@ -517,15 +647,17 @@ __global__ void __launch_bounds__(1024) merge_scan_kernel(DevBatch b) {
 }
 
 // Phase 1 (thread = bucket): stream offsets of every bucket of the block, pseudo records, per-contig offsets.
-// Phase 2 (thread = record): the block's raw records are spread evenly over the threads; each finds its bucket in the
-// shared prefix table, ranks itself among the bucket's records by (stream, time, mlen, seq) and writes its final form.
+// Phase 2 (thread = slot): the block's raw slots are spread evenly over the threads; each finds its bucket in the shared
+// prefix table; every candidate of the slot (one for a record, the kept bits of a mask entry) ranks itself among the
+// bucket's candidates of its stream by (time, mlen, seq) and is written in its final form.
 __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
-    __shared__ uint32_t s_off[8][MERGE_BLOCK];          // first raw record of (band, bucket)
-    __shared__ unsigned short s_n[8][MERGE_BLOCK];      // raw records of (band, bucket)
-    __shared__ uint32_t s_pre[MERGE_BLOCK + 1];         // exclusive prefix of the buckets' raw record counts
+    __shared__ uint32_t s_off[8][MERGE_BLOCK];          // first raw slot of (band, bucket)
+    __shared__ unsigned short s_n[8][MERGE_BLOCK];      // raw slots of (band, bucket)
+    __shared__ uint32_t s_pre[MERGE_BLOCK + 1];         // exclusive prefix of the buckets' raw slot counts
     __shared__ uint32_t s_dst[3][MERGE_BLOCK];          // first final record of (stream, bucket), relative to the block,
-                                                        // pseudo record and records of lower streams already discounted
+                                                        // pseudo record already discounted
     __shared__ int s_w[MERGE_BLOCK];
+    __shared__ int s_c[MERGE_BLOCK];
     __shared__ uint32_t s_wsum[MERGE_BLOCK / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long gb = b.gb_first + (long long)blockIdx.x * MERGE_BLOCK + tid;
@@ -544,7 +676,7 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
         for (int k = 0; k < 8; ++k)
             if (k < nbands) {
                 const Meta m = b.meta[(long long)k * b.n_buckets + gb];
-                const int n = meta_total(m);
+                const int n = meta_slots(m);
                 s_off[k][tid] = m.off;
                 s_n[k][tid] = (unsigned short)n;
                 nrec += (uint32_t)n;
@@ -556,7 +688,7 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     const BlockPartial bp = b.partial[blockIdx.x];
     const BlockPartial total = b.partial[b.n_merge_blocks];
     const long long sbase[3] = {0ll, (long long)total.sum[0], (long long)(total.sum[0] + total.sum[1])};
-    // block prefix of the raw record counts
+    // block prefix of the raw slot counts
     {
         uint32_t v = nrec;
         for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += t; }
@@ -568,12 +700,8 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
         if (tid == MERGE_BLOCK - 1) s_pre[MERGE_BLOCK] = pre + v;
     }
     s_w[tid] = bi.w;
-    {
-        const uint32_t lowerS = bi.n[0] - bi.pseudo[0], lowerA = lowerS + bi.n[1] - bi.pseudo[1];
-        s_dst[0][tid] = xs[0] + bi.pseudo[0];
-        s_dst[1][tid] = xs[1] + bi.pseudo[1] - lowerS;   // rank among all records of the bucket minus the lower streams
-        s_dst[2][tid] = xs[2] + bi.pseudo[2] - lowerA;
-    }
+    s_c[tid] = bi.c;
+    for (int s = 0; s < 3; ++s) s_dst[s][tid] = xs[s] + bi.pseudo[s];
     if (live) {
         long long o[3];
         for (int s = 0; s < 3; ++s) o[s] = (long long)bp.sum[s] + xs[s];
@@ -586,7 +714,7 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
                 const unsigned long long e = umax64(bp.emax[s - 1], xe[s - 1]);
                 long long ee = -1;
                 if (e != 0ull && (int)(e >> 32) == bi.c) ee = (long long)(e & 0xFFFFFFFFull) - 1;
-                b.dst[sbase[s] + o[s]] = pseudo_rec(bi.w, ee);
+                if (sbase[s] + o[s] < b.dst_cap) b.dst[sbase[s] + o[s]] = pseudo_rec(bi.w, ee);
             }
     }
     __syncthreads();
@@ -602,22 +730,42 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
         uint32_t idx = r - s_pre[bk];
         int band = 0;
         while (idx >= s_n[band][bk]) { idx -= s_n[band][bk]; ++band; }
-        const int4 rec = *reinterpret_cast<const int4*>(b.raw + s_off[band][bk] + idx);
-        const int st = (rec.z >> REC_STREAM_SHIFT) & 3;
-        const uint32_t key = ((uint32_t)st << 30) | (uint32_t)rec.w;
-        int rank = 0;
-        for (int k = 0; k < nbands; ++k) {
-            const int n = s_n[k][bk];
-            const int2* q = reinterpret_cast<const int2*>(reinterpret_cast<const int*>(b.raw + s_off[k][bk]) + 2);
-            for (int i = 0; i < n; ++i) {
-                const int2 zw = q[2 * i];  // .z, .w of record i (records are 16 bytes)
-                rank += ((((uint32_t)((zw.x >> REC_STREAM_SHIFT) & 3) << 30) | (uint32_t)zw.y) < key) ? 1 : 0;
+        const int4 v = *reinterpret_cast<const int4*>(b.raw + s_off[band][bk] + idx);
+        Rec rec;
+        rec.start = v.x; rec.end = v.y; rec.mflags = v.z; rec.key = v.w;
+        const int st = rec_stream(rec);
+        const bool is_entry = rec_is_entry(rec);
+        const int w = s_w[bk], mlen = rec_mlen(rec);
+        const long long dbase = sbase[st] + (long long)bp.sum[st] + s_dst[st][bk];
+        uint32_t bits = is_entry ? (uint32_t)rec.start : 1u;
+        const PlaneWord* cw = nullptr;
+        if (is_entry && bits) cw = b.planes + b.contigs[s_c[bk]].word_base;
+        while (bits) {
+            const int i = __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            const uint32_t key = is_entry ? entry_key(i, mlen) : (uint32_t)rec.key;
+            int rank = 0;
+            for (int k = 0; k < nbands; ++k) {
+                const int n = s_n[k][bk];
+                const int4* q = reinterpret_cast<const int4*>(b.raw + s_off[k][bk]);
+                for (int u = 0; u < n; ++u) {
+                    const int4 ov = q[u];
+                    Rec o;
+                    o.start = ov.x; o.end = ov.y; o.mflags = ov.z; o.key = ov.w;
+                    if (rec_stream(o) == st) rank += slot_count_below(o, key);
+                }
             }
+            Rec out;
+            if (is_entry) {
+                entry_interval(rec, w, cw, i, out.start, out.end);
+                out.mflags = mlen;
+                out.key = 32 * w + i;
+            } else {
+                out = finalize_rec(rec, w);
+            }
+            const long long at = dbase + rank;
+            if (at < b.dst_cap) *reinterpret_cast<int4*>(b.dst + at) = make_int4(out.start, out.end, out.mflags, out.key);
         }
-        int4 o4;
-        o4.x = rec.x; o4.y = rec.y; o4.z = rec.z & ((1 << REC_STREAM_SHIFT) - 1); o4.w = 32 * s_w[bk] + (rec.w >> 18);
-        const uint32_t rel = s_dst[st][bk] + (uint32_t)rank;  // 32-bit wrap-around: s_dst may hold "offset - lower"
-        *reinterpret_cast<int4*>(b.dst + sbase[st] + (long long)bp.sum[st] + rel) = o4;
     }
 }
 

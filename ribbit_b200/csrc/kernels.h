@@ -16,6 +16,12 @@ struct BlockPartial {
     unsigned long long emax[2];  // contig << 32 | elided_end_code, streams S and A
 };
 
+// per-bucket summary merge_count leaves for merge_write: records per stream (pseudo records excluded), elided maxima
+struct BucketSum {
+    unsigned short n[3];
+    unsigned char dS, dA;  // dmax of the bucket per window stream (merge_core.h); bit 7 of dS: slow bucket
+};
+
 struct DevBatch {
     BandLayout lay;
     int n_contigs;
@@ -38,12 +44,14 @@ struct DevBatch {
     const int* item_cap;            // [n_items]
     int* item_count;                // [n_items] records the item produced (may exceed item_cap: overflow)
     Meta* meta;                     // [nbands][n_buckets]
-    Rec* raw;                       // raw record pool
-    int* counters;                  // [0] overflowed items, [1] warm-up restarts
+    BucketSum* bsum;                // [n_buckets]
+    Rec* raw;                       // raw slot pool
+    int* counters;                  // [0] overflowed items, [1] warm-up restarts, [2] a count field overflowed (error)
     // merge
     BlockPartial* partial;          // [n_merge_blocks + 1]; after M2: exclusive prefixes, last = totals
     int n_merge_blocks;
     Rec* dst;                       // final pool: stream P, then S, then A
+    long long dst_cap;              // records the final pool holds (writes beyond it are dropped: the host re-runs M3)
     long long* contig_off;          // [3][n_contigs + 1]
     long long* totals;              // [3]
 };

@@ -13,14 +13,6 @@
 
 namespace rb {
 
-RB_HD int popc32(uint32_t x) {
-#ifdef __CUDA_ARCH__
-    return __popc(x);
-#else
-    return __builtin_popcount(x);
-#endif
-}
-
 // plane word w of a contig; words past the contig read as the guard word (all N). w >= -1 always (the guard in front).
 RB_HD PlaneWord motif_ldw(const PlaneWord* __restrict__ cw, int w, int nw) {
     const int i = w < nw ? w : nw;

@@ -48,6 +48,7 @@ enum : int {
     REC_DROPPED = 1,   // below the consumer's length cutoff: only advances the consumer's cursors
     REC_PSEUDO = 2,    // synthetic cursor-advance record (end = max end of elided dropped candidates)
     REC_NOCOMMIT = 4,  // anchored tail flush whose returned cursors the reference discards
+    REC_ENTRY = 8,     // raw pool only: a mask entry of a fast word (merge_core.h), expanded by the ordered compaction
 };
 static const int LEN_SAT = 1 << 24;
 
@@ -69,6 +70,13 @@ RB_HD int clz32(uint32_t x) {
     return __clz((int)x);
 #else
     return x ? __builtin_clz(x) : 32;
+#endif
+}
+RB_HD int popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
 #endif
 }
 // low 32 bits of (hi:lo) >> k, 0 <= k < 32
@@ -113,35 +121,43 @@ struct LaneCfg {
     int cutA;    // anchored keep cutoff                                          parse_anchored_shiftxor.cpp:572-573
     int wm;      // first word whose anchor view differs from X_s (positions >= L-s are forced to 1); per contig
     uint32_t dA; // smear shifts of the anchored keep filter, 6 bits each (smear_shifts)
-    uint32_t dA2;
 };
 
-// Shifts d_0..d_6 (each <= 32) that smear a bit over exactly n positions by doubling: with c_0 = 1,
-// d_i = min(c_i, n - c_i), c_{i+1} = c_i + d_i. Packed 6 bits each: d_0..d_4 in lo, d_5..d_6 in hi.
-// n > 96 cannot be reached with 7 steps of at most 32: returns 0 shifts (filter disabled, exact check per event).
-RB_HD void smear_shifts(int n, uint32_t& lo, uint32_t& hi) {
-    lo = 0u; hi = 0u;
-    if (n < 1 || n > 96) return;
+// consumer cutoffs
+RB_HD int cut_perfect(int m) { return m <= 6 ? 12 - m : m; }        // parse_perfect_shiftxor.cpp:193,216
+RB_HD int cut_subst(int m) { return m > 30 ? m / 3 : 10; }          // parse_substitute_shiftxor.cpp:423
+RB_HD int cut_anch(int m) {                                         // parse_anchored_shiftxor.cpp:572-573
+    int c = m > 6 ? m : 10;
+    if (m >= 10) c = (int)(0.9 * m);
+    return c;
+}
+static const int SMEAR_MAX = 16;  // positions the anchored keep filter looks back (exact for cutoffs up to this)
+
+// Shifts d_0..d_3 that smear a bit over exactly n <= 16 positions by doubling: with c_0 = 1, d_i = min(c_i, n - c_i),
+// c_{i+1} = c_i + d_i. Packed 6 bits each.
+RB_HD uint32_t smear_shifts(int n) {
+    uint32_t lo = 0u;
+    if (n < 1) n = 1;
+    if (n > SMEAR_MAX) n = SMEAR_MAX;
     int c = 1;
-    for (int i = 0; i < 7; ++i) {
-        int d = (n - c < c) ? n - c : c;
-        if (d > 32) d = 32;
-        if (i < 5) lo |= (uint32_t)d << (6 * i); else hi |= (uint32_t)d << (6 * (i - 5));
+    for (int i = 0; i < 4; ++i) {
+        const int d = (n - c < c) ? n - c : c;
+        lo |= (uint32_t)d << (6 * i);
         c += d;
     }
+    return lo;
 }
 
 RB_HD LaneCfg make_lane_cfg(int s, int m_lo, int m_hi, int s_lo, int s_hi, int band_m0, int band_m1) {
     LaneCfg c;
     c.s = (s >= s_lo && s <= s_hi && s >= 1) ? s : 0;
     c.motif = (c.s != 0 && s >= m_lo && s <= m_hi && s >= band_m0 && s <= band_m1) ? 1 : 0;
-    c.cutP = (s <= 6) ? 12 - s : s;
+    c.cutP = cut_perfect(s);
     c.cutPN = (s <= 6) ? 12 - s : s + (s - s_lo);
-    c.cutS = (s > 30) ? s / 3 : 10;
-    c.cutA = (s > 6) ? s : 10;
-    if (s >= 10) c.cutA = (int)(0.9 * s);
+    c.cutS = cut_subst(s);
+    c.cutA = cut_anch(s);
     c.wm = 0;
-    smear_shifts(c.cutA, c.dA, c.dA2);
+    c.dA = smear_shifts(c.cutA);
     return c;
 }
 // per-contig part of the lane configuration
@@ -272,47 +288,55 @@ RB_HD uint32_t anchor_word(const PlaneWord* cw, int w, int L, int s, uint32_t xa
     return a | keep;
 }
 
-// carries of the bit-sliced "number of mismatches in the last 8 positions" counters (previous word)
-// The window tests need, of the previous word, only the top 1 / 2 / 4 bits of the bit-sliced partial counts; those
-// bits are functions of the previous word's zero mask alone (its top 7 bits), so the lane carries just that mask and
-// recomputes the partial counts (plain shifts: they issue on the FMA pipe), instead of carrying five or six words.
-struct WinCarry {
-    uint32_t z;
+// Bit-sliced "number of mismatches in the last 8 positions". z = ~Y is the mismatch mask; per position t
+//   o1 / t1 : at least one / two zeros among z[t-1..t]        o2 / t2 / u2 : at least one / two / three among z[t-3..t]
+// The previous word's partial counts are carried (only their top bits are read, through funnel shifts).
+struct WinCarryS {
+    uint32_t o1, t1, o2, t2;
 };
-
-// fail mask for ">= 7 of 8" (substitution pass): bit p set iff Y[p-7..p] holds >= 2 zeros
-RB_HD uint32_t fail_ge2(uint32_t y, WinCarry& c) {
-    const uint32_t z = ~y, zp = c.z;
+struct WinCarryA {
+    uint32_t b, o1, t1, o2, t2, u2;  // b = the previous word of Y itself
+};
+// carries as if the previous word had the mismatch mask zp (exact in the top bits, which is all that is read)
+RB_HD void win_carry_init(WinCarryS& c, uint32_t zp) {
     const uint32_t zp1 = zp << 1;
-    const uint32_t o1p = zp | zp1, t1p = zp & zp1;             // exact in the top bits, which is all that is read
-    const uint32_t o1p2 = o1p << 2;
-    const uint32_t o2p = o1p | o1p2, t2p = t1p | (t1p << 2) | (o1p & o1p2);
-    const uint32_t z1 = fsl(zp, z, 1);
-    const uint32_t o1 = z | z1, t1 = z & z1;
-    const uint32_t o1s = fsl(o1p, o1, 2), t1s = fsl(t1p, t1, 2);
+    c.o1 = zp | zp1; c.t1 = zp & zp1;
+    const uint32_t o1s = c.o1 << 2, t1s = c.t1 << 2;
+    c.o2 = c.o1 | o1s; c.t2 = c.t1 | t1s | (c.o1 & o1s);
+}
+RB_HD void win_carry_init(WinCarryA& c, uint32_t zp) {
+    const uint32_t zp1 = zp << 1;
+    c.b = ~zp;
+    c.o1 = zp | zp1; c.t1 = zp & zp1;
+    const uint32_t o1s = c.o1 << 2, t1s = c.t1 << 2;
+    c.o2 = c.o1 | o1s; c.t2 = c.t1 | t1s | (c.o1 & o1s);
+    c.u2 = (c.t1 & o1s) | (c.o1 & t1s);
+}
+
+// fail mask for ">= 7 of 8" (substitution pass): bit p set iff X[p-7..p] holds >= 2 zeros. l1 = fsl(x_prev, x, 1).
+// cand: the perfect-run ends that follow six ones (x[t] = 0, x[t-6..t-1] = 1; every perfect cutoff is >= 6).
+RB_HD uint32_t fail_ge2(uint32_t x, uint32_t l1, WinCarryS& c, uint32_t& cand) {
+    const uint32_t o1 = ~(x & l1), t1 = ~(x | l1);
+    const uint32_t o1s = fsl(c.o1, o1, 2), t1s = fsl(c.t1, t1, 2);
     const uint32_t o2 = o1 | o1s;
     const uint32_t t2 = t1 | t1s | (o1 & o1s);
-    const uint32_t o2s = fsl(o2p, o2, 4), t2s = fsl(t2p, t2, 4);
+    const uint32_t o2s = fsl(c.o2, o2, 4), t2s = fsl(c.t2, t2, 4);
     const uint32_t t3 = t2 | t2s | (o2 & o2s);
-    c.z = z;
+    cand = ~(x | fsl(c.o2, o2, 1) | fsl(c.o1, o1, 5));
+    c.o1 = o1; c.t1 = t1; c.o2 = o2; c.t2 = t2;
     return t3;
 }
-// fail mask for ">= 6 of 8" (anchored pass): bit p set iff Y[p-7..p] holds >= 3 zeros
-RB_HD uint32_t fail_ge3(uint32_t y, WinCarry& c) {
-    const uint32_t z = ~y, zp = c.z;
-    const uint32_t zp1 = zp << 1;
-    const uint32_t o1p = zp | zp1, t1p = zp & zp1;
-    const uint32_t o1p2 = o1p << 2, t1p2 = t1p << 2;
-    const uint32_t o2p = o1p | o1p2, t2p = t1p | t1p2 | (o1p & o1p2), u2p = (t1p & o1p2) | (o1p & t1p2);
-    const uint32_t z1 = fsl(zp, z, 1);
-    const uint32_t o1 = z | z1, t1 = z & z1;
-    const uint32_t o1s = fsl(o1p, o1, 2), t1s = fsl(t1p, t1, 2);
+// fail mask for ">= 6 of 8" (anchored pass): bit p set iff B[p-7..p] holds >= 3 zeros
+RB_HD uint32_t fail_ge3(uint32_t b, WinCarryA& c) {
+    const uint32_t l1 = fsl(c.b, b, 1);
+    const uint32_t o1 = ~(b & l1), t1 = ~(b | l1);
+    const uint32_t o1s = fsl(c.o1, o1, 2), t1s = fsl(c.t1, t1, 2);
     const uint32_t o2 = o1 | o1s;
     const uint32_t t2 = t1 | t1s | (o1 & o1s);
     const uint32_t u2 = (t1 & o1s) | (o1 & t1s);
-    const uint32_t o2s = fsl(o2p, o2, 4), t2s = fsl(t2p, t2, 4), u2s = fsl(u2p, u2, 4);
+    const uint32_t o2s = fsl(c.o2, o2, 4), t2s = fsl(c.t2, t2, 4), u2s = fsl(c.u2, u2, 4);
     const uint32_t u3 = u2 | u2s | (t2 & o2s) | (o2 & t2s);
-    c.z = z;
+    c.b = b; c.o1 = o1; c.t1 = t1; c.o2 = o2; c.t2 = t2; c.u2 = u2;
     return u3;
 }
 
@@ -348,13 +372,12 @@ RB_HD void ev_step(uint32_t P, EvCarry& c, uint32_t& S, uint32_t& E, uint32_t& S
 struct LaneState {
     uint32_t x_prev, x_cur, x_nxt;  // X_s of words w-1, w, w+1
     int lenL;                       // anchor-view run length ending at the end of word w-1
-    WinCarry cs, ca;
+    WinCarryS cs;
+    WinCarryA ca;
     int pst;                        // perfect machine: start of the open run or -1 (last_starts); slow words
-    int lastRS;                     // position of the latest run start of X_m; fast words
-    uint32_t pa2, pa6;              // previous word of "2 / 6 ones in a row ending here"
     WinState S, A;                  // valid while the previous word was a slow word
     EvCarry es, ea;                 // carries always valid; lastS valid while the previous word was a fast word
-    uint32_t sm[7];                 // anchored keep filter: previous word of each smear level
+    uint32_t sm[4];                 // anchored keep filter: previous word of each smear level
     XCache xc;
     // warm-up bookkeeping (chunks that do not start at the contig start)
     int sync;                       // bit0 anchors exact, bit1 perfect, bit2 subst, bit3 anchored
@@ -395,50 +418,31 @@ RB_HD void emit_perfect(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int sta
     sk.rec(STREAM_P, start, end, cfg.s, 0, ((time - 32 * it.w) << 18) | (cfg.s << 2));
 }
 
-// Anchored keep filter. M1[t] = OR of S[t-k], k = 1..cutA: an E bit with M1 set belongs to a component whose S bit
-// is at most cutA positions back, i.e. whose length t - ts - 1 is below the consumer's cutoff
-// (parse_anchored_shiftxor.cpp:153). Exact when the last four words were fast words.
+// Anchored keep filter. M1[t] = OR of S[t-k], k = 1..n, n = min(cutA, SMEAR_MAX): an E bit with M1 set belongs to a
+// component whose S bit is at most n positions back, i.e. whose length t - ts - 1 is below the consumer's cutoff
+// (parse_anchored_shiftxor.cpp:153). Exact for cutA <= SMEAR_MAX, else a prefilter (survivors are checked when the
+// entry is expanded, merge_core.h). Valid when this and the previous word are fast words.
 RB_HD uint32_t smear_step(const LaneCfg& cfg, LaneState& st, uint32_t S, uint32_t Sprev) {
     uint32_t v = fsl(Sprev, S, 1);
-#define RB_SMEAR_LEVEL(i, d)                                  \
-    {                                                         \
-        const uint32_t nv = v | fslc(st.sm[i], v, (int)(d)); \
-        st.sm[i] = v;                                         \
-        v = nv;                                               \
+#define RB_SMEAR_LEVEL(i, d)                                 \
+    {                                                        \
+        const uint32_t nv = v | fsl(st.sm[i], v, (int)(d)); \
+        st.sm[i] = v;                                        \
+        v = nv;                                              \
     }
     RB_SMEAR_LEVEL(0, cfg.dA & 63u)
     RB_SMEAR_LEVEL(1, (cfg.dA >> 6) & 63u)
     RB_SMEAR_LEVEL(2, (cfg.dA >> 12) & 63u)
     RB_SMEAR_LEVEL(3, (cfg.dA >> 18) & 63u)
-    RB_SMEAR_LEVEL(4, (cfg.dA >> 24) & 63u)
-    RB_SMEAR_LEVEL(5, cfg.dA2 & 63u)
-    RB_SMEAR_LEVEL(6, (cfg.dA2 >> 6) & 63u)
 #undef RB_SMEAR_LEVEL
-    return cfg.dA ? v : 0u;  // cutoffs outside the smear range: no filtering
+    return v;
 }
 
 // ---- fast word -----------------------------------------------------------------------------------------------------
-// Emits the components whose E bit lies in this word and that reach the consumer's length cutoff; the others only
-// contribute their emission time (Sink::dropped). S/E are this word's masks, Sprev the previous word's S mask.
-// Survivors of the keep filter (bits of x) of one stream, checked exactly and emitted: the component that ends at
-// E-bit i is (ls, le) = (ts - 7, p0 + i - 8), ts = the latest S bit before i. Returns the bits that were emitted.
-template <class Sink>
-RB_HD uint32_t kept_events(Sink& sk, int stream, int s, int cut, int p0, uint32_t S, uint32_t x, int lastS) {
-    uint32_t kept = 0u;
-    while (x) {
-        const int i = ctz32(x);
-        x &= x - 1u;
-        const uint32_t sb = S & lowmask(i);
-        const int ts = sb ? p0 + 31 - clz32(sb) : lastS;
-        const int ls = ts - 7, le = p0 + i - 8;
-        if (le - ls >= cut) {
-            sk.rec(stream, ls, le, s, 0, (i << 18) | (s << 2));
-            kept |= 1u << i;
-        }
-    }
-    return kept;
-}
-
+// A fast word hands its candidates over as MASK ENTRIES (Sink::entry): per stream the E bits (perfect stream: the run ends)
+// that survived the bit-parallel prefilters, the S mask (run starts) of the word and the position of the latest S bit in
+// front of the word. The ordered compaction expands them into records and applies the consumer's cutoff exactly
+// (merge_core.h entry_interval); E bits that fail it only contribute their emission time, like the prefiltered ones.
 // lastS of the bit-parallel view from the reference machine's state (slow word -> fast word)
 RB_HD void win_to_fast(const WinState& st, int& lastS) {
     if (st.ls != -1) lastS = st.ls + 7;
@@ -471,30 +475,35 @@ RB_HD bool win_from_fast(const EvCarry& c, int p0, WinState& st) {
     }
     return true;
 }
+// Start of the run of G = X_s & ~N that contains position 32*w + i - 1 (bit i-1 of x = X_s[w] is set, i in [1, 32], no N
+// in word w). Stateless: looks back over the earlier words as far as the run goes; this is the reference's last_starts
+// (parse_perfect_shiftxor.cpp:194-200) without carrying it.
+RB_HD int perfect_run_start(const PlaneWord* cw, int w, int i, int s, uint32_t x) {
+    const uint32_t zb = ~x & lowmask(i);  // zeros below bit i
+    if (zb) return 32 * w + 32 - clz32(zb);
+    for (int k = w - 1; k >= 0; --k) {
+        const uint32_t z = ~(x_word(cw, k, s) & ~cw[k].n);
+        if (z) return 32 * k + 32 - clz32(z);
+    }
+    return 0;
+}
+
 // All three machines of a motif lane at a fast -> slow transition in front of word w (x_prev = X_m[w-1] already rotated).
 // The new state is returned apart from the lane state: the caller applies it only if every lane of the item succeeded.
 struct SlowEntry {
     WinState S, A;
     int pst;
 };
-RB_HD bool lane_to_slow(const LaneCfg& cfg, const LaneState& st, int w, SlowEntry& e) {
+RB_HD bool lane_to_slow(const LaneCfg& cfg, const LaneState& st, const PlaneWord* cw, int w, SlowEntry& e) {
     e.S = st.S; e.A = st.A; e.pst = st.pst;
     if (!cfg.motif) return true;
     if (!win_from_fast(st.es, 32 * (w - 1), e.S) || !win_from_fast(st.ea, 32 * (w - 1), e.A)) return false;
-    e.pst = (st.x_prev >> 31) ? st.lastRS : -1;  // the run that is open at the word boundary (parse_perfect_shiftxor.cpp:194)
+    // the run that is open at the word boundary (parse_perfect_shiftxor.cpp:194)
+    e.pst = (st.x_prev >> 31) ? perfect_run_start(cw, w - 1, 32, cfg.s, st.x_prev) : -1;
     return true;
 }
 RB_HD void lane_enter_slow(LaneState& st, const SlowEntry& e) { st.S = e.S; st.A = e.A; st.pst = e.pst; }
 
-// "six ones in a row ending at t" of X_m, with carries; kept up to date in every word (fast and slow)
-RB_HD uint32_t six_ones(uint32_t x, uint32_t xs1, uint32_t& pa2, uint32_t& pa6) {
-    const uint32_t a2 = x & xs1;
-    const uint32_t a4 = a2 & fsl(pa2, a2, 2);
-    const uint32_t a6 = a4 & fsl(pa2, a2, 4);
-    const uint32_t a6s1 = fsl(pa6, a6, 1);  // six ones ending at t-1
-    pa2 = a2; pa6 = a6;
-    return a6s1;
-}
 // ---- slow word: the reference state machines bit by bit ----------------------------------------------------------
 template <class Sink>
 RB_HD void win_slow_bit(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int stream, int p, int nbit, int vbit, int pass,
@@ -662,15 +671,17 @@ RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const Pla
     return lane_phase1_fast_t<true>(cfg, st, cw, w, L, &v_next, &sp, small);
 }
 
-// Phase 2 of a fast word (it.slow == 0, machines on) (it.slow == 0, it.emit_on == 1, machines on): every window is evaluated, so
-// o.v is all ones and the N plane is not consulted.
+// Phase 2 of a fast word (it.slow == 0, machines on): every window is evaluated, so o.v is all ones and the N plane is
+// not consulted.
 template <class Sink>
 RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const IterCtx& it, uint32_t a_m2, uint32_t a_m1,
                             uint32_t a_p1, uint32_t a_p2) {
     if (cfg.motif) {
         const uint32_t x = st.x_cur;
+        const uint32_t l1 = fsl(st.x_prev, x, 1);
         const uint32_t b = x | a_m2 | a_m1 | a_p1 | a_p2;
-        const uint32_t passS = ~fail_ge2(x, st.cs);
+        uint32_t cand;
+        const uint32_t passS = ~fail_ge2(x, l1, st.cs, cand);
         const uint32_t passA = ~fail_ge3(b, st.ca);
         uint32_t sS, eS, sSp, sA, eA, sAp;
         ev_step(passS, st.es, sS, eS, sSp);
@@ -679,41 +690,25 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const I
         if (it.prev_slow) {
             win_to_fast(st.S, st.es.lastS);
             win_to_fast(st.A, st.ea.lastS);
-            if (st.pst >= 0) st.lastRS = st.pst;  // the run that is open at the word boundary
         }
         if (!it.emit_on) {
-            // warm-up in fast words: pst is exact once a mismatch was seen; lastS once a component start was seen
-            // or nine windows in a row failed (any later component starts inside the scanned range)
-            if (x != 0xFFFFFFFFu) st.sync |= SYNC_P;
+            // warm-up in fast words: lastS is exact once a component start was seen or nine windows in a row failed (any
+            // later component starts inside the scanned range); the perfect stream keeps no state in fast words
+            st.sync |= SYNC_P;
             if (sS != 0u || nine_fails(~passS, st.zS)) st.sync |= SYNC_S;
             if (sA != 0u || nine_fails(~passA, st.zA)) st.sync |= SYNC_A;
         }
-        // candidates of this word: everything that needs per-bit work is gathered into one rarely taken region
         const int p0 = 32 * it.w;
-        const uint32_t xs1 = fsl(st.x_prev, x, 1);
-        const uint32_t sx = x & ~xs1;                                           // perfect runs start here
-        const uint32_t cand = ~x & xs1 & six_ones(x, xs1, st.pa2, st.pa6);     // run ends that follow six ones
-        // the smear looks back up to three words: trust it once four fast words in a row were seen
-        // substitution cutoff is >= 10 (parse_substitute_shiftxor.cpp:423): a component whose S bit is 9 or 10 back
-        // has length 8 or 9 and is below it
+        // prefilters: a substitution component whose S bit is 9 or 10 back has length 8 or 9, below every cutoff
+        // (parse_substitute_shiftxor.cpp:423: >= 10); the smear looks back into the previous word: trust it once a few
+        // fast words in a row were seen
         const uint32_t xS = it.emit_on ? (eS & ~(fsl(sSp, sS, 9) | fsl(sSp, sS, 10))) : 0u;
         const uint32_t xA = it.emit_on ? (eA & ~(it.fastrun >= 4 ? killA : 0u)) : 0u;
-        uint32_t keptS = 0u, keptA = 0u;
-        if (cand | xS | xA) {
-            uint32_t c = cand;
-            while (c) {  // perfect runs (parse_perfect_shiftxor.cpp:190-208): every cutoff is >= 6
-                const int i = ctz32(c);
-                c &= c - 1u;
-                const uint32_t sb = sx & lowmask(i);
-                const int a = sb ? p0 + 31 - clz32(sb) : st.lastRS;
-                if (p0 + i - a >= cfg.cutP) emit_perfect(sk, it, cfg, a, p0 + i, p0 + i);
-            }
-            keptS = kept_events(sk, STREAM_S, cfg.s, cfg.cutS, p0, sS, xS, st.es.lastS);
-            keptA = kept_events(sk, STREAM_A, cfg.s, cfg.cutA, p0, sA, xA, st.ea.lastS);
-        }
-        sk.dropped_mask(STREAM_S, eS & ~keptS);
-        sk.dropped_mask(STREAM_A, eA & ~keptA);
-        st.lastRS = sx ? p0 + 31 - clz32(sx) : st.lastRS;
+        if (it.emit_on && cand) sk.entry(STREAM_P, cfg.s, cand, x & ~l1, 0);
+        if (xS) sk.entry(STREAM_S, cfg.s, xS, sS, st.es.lastS);
+        if (xA) sk.entry(STREAM_A, cfg.s, xA, sA, st.ea.lastS);
+        sk.dropped_mask(STREAM_S, eS & ~xS);
+        sk.dropped_mask(STREAM_A, eA & ~xA);
         st.es.lastS = sS ? p0 + 31 - clz32(sS) : st.es.lastS;
         st.ea.lastS = sA ? p0 + 31 - clz32(sA) : st.ea.lastS;
     }
@@ -733,13 +728,13 @@ RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneW
         const PlaneWord o = cw[it.w];
         const uint32_t x = st.x_cur;
         const uint32_t b = x | a_m2 | a_m1 | a_p1 | a_p2;
-        const uint32_t passS = ~fail_ge2(x, st.cs) & o.v;
+        uint32_t cand;
+        const uint32_t passS = ~fail_ge2(x, fsl(st.x_prev, x, 1), st.cs, cand) & o.v;
         const uint32_t passA = ~fail_ge3(b, st.ca) & o.v;
         uint32_t sS, eS, sSp, sA, eA, sAp;
         ev_step(passS, st.es, sS, eS, sSp);
         ev_step(passA, st.ea, sA, eA, sAp);
         (void)smear_step(cfg, st, sA, sAp);
-        (void)six_ones(x, fsl(st.x_prev, x, 1), st.pa2, st.pa6);
         if (machines_on) {
             {
                 const uint32_t prev_v31 = cw[it.w - 1].v >> 31;
@@ -790,10 +785,9 @@ RB_HD void lane_tail(Sink& sk, const LaneCfg& cfg, LaneState& st, int L) {
 // start whose state becomes exact once the sync bits are set.
 RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int q) {
     st.x_prev = 0u; st.x_cur = 0u; st.x_nxt = 0u; st.lenL = 0;
-    st.cs.z = 0u;
-    st.ca = st.cs;
+    win_carry_init(st.cs, 0u);
+    win_carry_init(st.ca, 0u);
     st.pst = -1;
-    st.lastRS = -1; st.pa2 = st.pa6 = 0u;
     st.S.cur = st.S.ls = st.S.le = -1;
     st.A = st.S;
     // nothing before the contig start: "failing" windows; a cold start must not invent a run of failing windows
@@ -802,7 +796,7 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
     st.es.S = 0u;
     st.es.lastS = -1;
     st.ea = st.es;
-    for (int i = 0; i < 7; ++i) st.sm[i] = 0u;
+    for (int i = 0; i < 4; ++i) st.sm[i] = 0u;
     st.xc.h = st.xc.l = 0u; st.xc.idx = -0x40000000;
     st.sync = (q == 0) ? SYNC_ALL : 0;
     st.zS = st.zA = 0;
@@ -810,8 +804,8 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
     st.x_cur = x_word(cw, q, cfg.s);
     if (q > 0) {
         st.x_prev = x_word(cw, q - 1, cfg.s);
-        st.cs.z = ~st.x_prev;
-        st.ca.z = ~st.x_prev;
+        win_carry_init(st.cs, ~st.x_prev);
+        win_carry_init(st.ca, ~st.x_prev);
     }
 }
 

@@ -1,0 +1,179 @@
+// ribbit-b200: per-lane logic of the TIGHT LOOP of the scan kernel — consecutive fast words of an item, the bulk of every
+// contig. Same mapping and same results as the general path (scan_core.h: lane = shift, fast-word logic of
+// lane_phase1_fast / lane_phase2_fast), written for a minimal instruction stream:
+//   * all carries of the bit-sliced window counters, of the component start / end detection and of the keep filter stay
+//     in registers in their funnel-shift-ready form (TightState); nothing is recomputed from the previous word;
+//   * no per-bit work and no per-lane loops: a lane's candidates leave as mask entries (merge_core.h), the consumer's
+//     cutoff is applied when the ordered compaction expands them;
+//   * anchors (parse_anchored_shiftxor.cpp:20-56) in straight-line code; the run-length bound "< 2s" is only evaluated
+//     when a lane of the item sees a run that could reach it (bands whose smallest shift is >= 17: a half word of ones;
+//     the band with the small shifts: exact edge logic), which is rare outside repeats;
+//   * the substitution stream's event logic is skipped while no lane of the item has a passing window.
+// Shared with the CPU warp emulator (tests/emu/emu_scan.cpp), which runs these functions lane by lane.
+#ifndef RB_SCAN_TIGHT_H
+#define RB_SCAN_TIGHT_H
+
+#include "scan_core.h"
+
+namespace rb {
+
+struct TightCfg {
+    int s, sh;           // shift, s & 31
+    int K2;              // 2 s (anchor run-length bound)
+    uint32_t amask;      // ~0 for lanes that own a shift, 0 for idle lanes (their anchors must read as 0)
+    uint32_t mmask;      // ~0 for motif lanes
+    int d0, d1, d2, d3;  // smear shifts of the anchored keep filter (SMALL items; else 1, 2, 4, 8)
+    int e0, e1, e2, e3, e4;  // doubling shifts of "K2 ones in a row" (SMALL items)
+};
+
+struct TightState {
+    uint32_t xp, xc;       // X_s of words w-1, w
+    uint32_t bh, bl;       // h / l of the plane word that was the "b" operand of X_s[w]
+    int lenL;              // SMALL: anchor-view run length ending at the end of word w-1
+    WinCarryS cs;
+    WinCarryA ca;
+    EvCarry es, ea;
+    uint32_t sm[4];
+};
+
+RB_HD TightCfg make_tight_cfg(const LaneCfg& c) {
+    TightCfg t;
+    t.s = c.s; t.sh = c.s & 31; t.K2 = 2 * c.s;
+    t.amask = c.s ? 0xFFFFFFFFu : 0u;
+    t.mmask = c.motif ? 0xFFFFFFFFu : 0u;
+    t.d0 = (int)(c.dA & 63u); t.d1 = (int)((c.dA >> 6) & 63u); t.d2 = (int)((c.dA >> 12) & 63u); t.d3 = (int)((c.dA >> 18) & 63u);
+    // five doubling steps reach min(K2, 32) ones in a row
+    int k = 1, e[5];
+    for (int i = 0; i < 5; ++i) {
+        int sh = t.K2 - k;
+        sh = sh < k ? sh : k;
+        sh = sh < 0 ? 0 : sh;
+        e[i] = sh;
+        k += sh;
+    }
+    t.e0 = e[0]; t.e1 = e[1]; t.e2 = e[2]; t.e3 = e[3]; t.e4 = e[4];
+    return t;
+}
+
+RB_HD void tight_enter(const LaneCfg& cfg, const LaneState& st, TightState& t) {
+    t.xp = st.x_prev; t.xc = st.x_cur; t.bh = st.xc.h; t.bl = st.xc.l; t.lenL = st.lenL;
+    t.cs = st.cs; t.ca = st.ca; t.es = st.es; t.ea = st.ea;
+    for (int i = 0; i < 4; ++i) t.sm[i] = st.sm[i];
+    if (!cfg.motif) {
+        // the general path keeps no event state for shifts that are not motif sizes: theirs reads "nothing ever passed"
+        t.es.P = 0u; t.es.S = 0u; t.es.r2 = t.es.r4 = t.es.r8 = 0xFFFFFFFFu; t.es.lastS = -1;
+        t.ea = t.es;
+        for (int i = 0; i < 4; ++i) t.sm[i] = 0u;
+    }
+}
+RB_HD void tight_leave(const TightState& t, LaneState& st) {
+    st.x_prev = t.xp; st.x_cur = t.xc; st.xc.h = t.bh; st.xc.l = t.bl; st.lenL = t.lenL;
+    st.cs = t.cs; st.ca = t.ca; st.es = t.es; st.ea = t.ea;
+    for (int i = 0; i < 4; ++i) st.sm[i] = t.sm[i];
+}
+
+// ---- phase A: X_s[w+1] and the anchor word A_s[w] ---------------------------------------------------------------------
+// oh / ol = h / l of plane word w+1 (the same for every lane), bh / bl = h / l of plane word w + 1 + (s >> 5) + 1.
+// Returns the straight-line anchor word; `sus` tells that some run touching the word may reach 2s positions (or that the
+// word / its successor is all ones), in which case the item recomputes the word with tight_anchor_exact.
+template <bool SMALL>
+RB_HD uint32_t tight_phaseA(const TightCfg& c, TightState& t, uint32_t oh, uint32_t ol, uint32_t bh, uint32_t bl, uint32_t& xn,
+                            uint32_t& l1, bool& sus) {
+    xn = ~((oh ^ fsr(t.bh, bh, c.sh)) | (ol ^ fsr(t.bl, bl, c.sh)));
+    t.bh = bh; t.bl = bl;
+    const uint32_t x = t.xc;
+    l1 = fsl(t.xp, x, 1);
+    const uint32_t l2 = fsl(t.xp, x, 2), r1 = fsr(x, xn, 1), r2 = fsr(x, xn, 2);
+    // positions of X_s that lie in a run of at least 3 (anchor_size, parse_anchored_shiftxor.cpp:44)
+    uint32_t a = x & ((l1 & (l2 | r1)) | (r1 & r2)) & c.amask;
+    if (!SMALL) {
+        // 2s >= 50 here: a run of that length touching word w covers an aligned half word of w-1, w or w+1; the caller
+        // keeps the flags of the two previous words
+        const uint32_t u = ~xn;
+        sus = (((u - 0x00010001u) & xn & 0x80008000u) != 0u);
+        return a;
+    }
+    sus = (x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu);
+    // runs that touch a word edge: their full length is known from the neighbours
+    const int lead = ctz32(~x), trail = clz32(~x), leadn = ctz32(~xn);
+    a &= (t.lenL + lead >= c.K2) ? ~lowmask(lead) : 0xFFFFFFFFu;
+    a &= (trail + leadn >= c.K2) ? lowmask(32 - trail) : 0xFFFFFFFFu;
+    // a run inside the word can be too long as well: K2 ones in a row by doubling (32 ones in a row cannot occur when
+    // !sus, so lanes with K2 > 30 end with e == 0)
+    uint32_t e = x;
+    e &= e >> c.e0; e &= e >> c.e1; e &= e >> c.e2; e &= e >> c.e3; e &= e >> c.e4;
+    if (e) {
+        uint32_t d = e;
+        for (int k = 1; k < c.K2;) { const int sh = (k < c.K2 - k) ? k : c.K2 - k; d |= d << sh; k += sh; }
+        a &= ~d;
+    }
+    t.lenL = trail;  // meaningless when sus: tight_anchor_exact sets it
+    return a;
+}
+
+// Length of the run of ones of X_s that ends at the end of word w-1 (t.xp = X_s[w-1]), looked up in the planes when that
+// word is all ones; saturates above K2 + 32. Used where the run length is not carried (items without small shifts).
+RB_HD int tight_lenL_lookup(const TightCfg& c, const TightState& t, const PlaneWord* cw, int w) {
+    int lenL = clz32(~t.xp);
+    if (lenL == 32)
+        for (int k = w - 2; k >= 0; --k) {
+            const int tr = clz32(~x_word(cw, k, c.s));
+            lenL += tr;
+            if (tr < 32 || lenL >= c.K2 + 32) break;
+        }
+    return lenL;
+}
+
+// Exact anchor word for a word tight_phaseA flagged (any lane of the item): the general anchor_word with the run length in
+// front of the word looked up in the planes when the previous word is all ones.
+template <bool SMALL>
+RB_HD uint32_t tight_anchor_exact(const TightCfg& c, TightState& t, const PlaneWord* cw, int w, int L, uint32_t xn, int lenL_in) {
+    if (!c.s) return 0u;
+    int lenL = SMALL ? lenL_in : tight_lenL_lookup(c, t, cw, w);
+    const uint32_t a = anchor_word(cw, w, L, c.s, t.xc, xn, lenL);
+    t.lenL = lenL;
+    return a;
+}
+
+// ---- phase B: window tests, component events, keep filter ---------------------------------------------------------------
+// an = A_{m-2} | A_{m-1} | A_{m+1} | A_{m+2}. Non-motif lanes produce all-zero masks.
+RB_HD void tight_windows(const TightCfg& c, TightState& t, uint32_t an, uint32_t l1, uint32_t& passS, uint32_t& passA, uint32_t& cand) {
+    const uint32_t x = t.xc;
+    passS = ~fail_ge2(x, l1, t.cs, cand) & c.mmask;
+    passA = ~fail_ge3(x | an, t.ca) & c.mmask;
+}
+
+struct TightOut {
+    uint32_t x, s, el;  // surviving E bits, S mask of the word, E bits the prefilter elided
+    int last;           // position of the latest S bit in front of the word
+};
+template <bool SMALL>
+RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t passA, TightOut& o) {
+    uint32_t sA, eA, sAp;
+    ev_step(passA, t.ea, sA, eA, sAp);
+    uint32_t v = fsl(sAp, sA, 1);
+#define RB_TSMEAR(i, d)                                  \
+    {                                                    \
+        const uint32_t nv = v | fsl(t.sm[i], v, (d));   \
+        t.sm[i] = v;                                     \
+        v = nv;                                          \
+    }
+    if (SMALL) { RB_TSMEAR(0, c.d0) RB_TSMEAR(1, c.d1) RB_TSMEAR(2, c.d2) RB_TSMEAR(3, c.d3) }
+    else { RB_TSMEAR(0, 1) RB_TSMEAR(1, 2) RB_TSMEAR(2, 4) RB_TSMEAR(3, 8) }
+#undef RB_TSMEAR
+    o.x = eA & ~v; o.el = eA & v; o.s = sA; o.last = t.ea.lastS;
+    t.ea.lastS = sA ? p0 + 31 - clz32(sA) : t.ea.lastS;
+}
+RB_HD void tight_events_S(TightState& t, int p0, uint32_t passS, TightOut& o) {
+    uint32_t sS, eS, sSp;
+    ev_step(passS, t.es, sS, eS, sSp);
+    // a substitution component whose S bit is 9 or 10 back has length 8 or 9: below every cutoff
+    o.x = eS & ~(fsl(sSp, sS, 9) | fsl(sSp, sS, 10));
+    o.el = eS & ~o.x; o.s = sS; o.last = t.es.lastS;
+    t.es.lastS = sS ? p0 + 31 - clz32(sS) : t.es.lastS;
+}
+// rotation at the end of a step
+RB_HD void tight_rotate(TightState& t, uint32_t xn) { t.xp = t.xc; t.xc = xn; }
+
+}  // namespace rb
+#endif

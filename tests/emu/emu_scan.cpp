@@ -13,6 +13,7 @@
 #include "motif_core.h"
 #include "merge_core.h"
 #include "scan_core.h"
+#include "scan_tight.h"
 
 using namespace rb;
 
@@ -24,15 +25,19 @@ struct ItemOut {
 
 struct EmuSink {
     ItemOut* out;
-    uint32_t counts;
+    int nslots;
     int dmax[3];
     void rec(int stream, int start, int end, int mlen, int flags, int key) {
         Rec r; r.start = start; r.end = end; r.mflags = mlen | (flags << 16) | (stream << REC_STREAM_SHIFT); r.key = key;
         out->raw.push_back(r);
-        counts += 1u << (10 * stream);
+        ++nslots;
     }
-    void dropped(int stream, int tw) { if (tw + 1 > dmax[stream]) dmax[stream] = tw + 1; }
-    void dropped_mask(int stream, uint32_t el) { if (el) dropped(stream, 31 - clz32(el)); }
+    void entry(int stream, int mlen, uint32_t mask, uint32_t smask, int last) {
+        out->raw.push_back(make_entry(stream, mlen, mask, smask, last));
+        ++nslots;
+    }
+    void dropped_mask(int stream, uint32_t el) { if (el) dmax[stream] = std::max(dmax[stream], 32 - clz32(el)); }
+    void reset(ItemOut* o) { out = o; nslots = 0; dmax[0] = dmax[1] = dmax[2] = 0; }
 };
 
 void pack(const char* seq, int64_t L, int guard, std::vector<PlaneWord>& pw) {
@@ -61,6 +66,69 @@ void pack(const char* seq, int64_t L, int guard, std::vector<PlaneWord>& pw) {
     }
 }
 
+
+// The kernel's tight_run for one item: the lanes step through scan_tight.h in lockstep, the warp-level operations
+// (votes, shuffles, ballots, reductions) are done across the lane arrays.
+template <bool SMALL>
+long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const PlaneWord* cw, int& w, int wend, int L, ItemOut& io,
+               std::vector<Meta>& meta) {
+    const int bw = lay.bw;
+    TightState ts[32];
+    TightCfg tc[32];
+    for (int j = 0; j < bw; ++j) { tight_enter(cfg[j], st[j], ts[j]); tc[j] = make_tight_cfg(cfg[j]); }
+    uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
+    bool susp = true, susc = true;
+    int zc = 0;
+    long steps = 0;
+    const int w_in = w;
+    while (w < wend && (vprev & vcur) == 0xFFFFFFFFu) {
+        uint32_t a[32], xn[32], l1[32], pair[32];
+        int lenL0[32];
+        bool rare = false;
+        for (int j = 0; j < bw; ++j) {
+            const PlaneWord o = cw[w + 1], b = cw[w + 1 + (tc[j].s >> 5) + 1];
+            bool sus;
+            lenL0[j] = ts[j].lenL;
+            a[j] = tight_phaseA<SMALL>(tc[j], ts[j], o.h, o.l, b.h, b.l, xn[j], l1[j], sus);
+            rare |= sus;
+        }
+        if (!SMALL) { const bool r3 = rare | susc | susp; susp = susc; susc = rare; rare = r3; }
+        if (rare) for (int j = 0; j < bw; ++j) a[j] = tight_anchor_exact<SMALL>(tc[j], ts[j], cw, w, L, xn[j], lenL0[j]);
+        for (int j = 0; j < bw; ++j) pair[j] = a[j] | a[j + 1 < bw ? j + 1 : j];
+        uint32_t passS[32], passA[32], cand[32];
+        TightOut oa[32], os[32];
+        bool actS = false;
+        for (int j = 0; j < bw; ++j) {
+            const uint32_t an = pair[j >= 2 ? j - 2 : j] | pair[j + 1 < bw ? j + 1 : j];
+            tight_windows(tc[j], ts[j], an, l1[j], passS[j], passA[j], cand[j]);
+            tight_events_A<SMALL>(tc[j], ts[j], 32 * w, passA[j], oa[j]);
+            actS |= passS[j] != 0u;
+        }
+        for (int j = 0; j < bw; ++j) {
+            os[j].x = os[j].s = os[j].el = 0u; os[j].last = 0;
+            if (actS || zc < 2) tight_events_S(ts[j], 32 * w, passS[j], os[j]);
+            cand[j] &= tc[j].mmask;
+        }
+        if (actS || zc < 2) zc = actS ? 0 : zc + 1;
+        const uint32_t off = (uint32_t)io.raw.size();
+        uint32_t elA = 0u, elS = 0u;
+        for (int j = 0; j < bw; ++j) if (oa[j].x) io.raw.push_back(make_entry(STREAM_A, tc[j].s, oa[j].x, oa[j].s, oa[j].last));
+        for (int j = 0; j < bw; ++j) if (os[j].x) io.raw.push_back(make_entry(STREAM_S, tc[j].s, os[j].x, os[j].s, os[j].last));
+        for (int j = 0; j < bw; ++j) if (cand[j]) io.raw.push_back(make_entry(STREAM_P, tc[j].s, cand[j], ts[j].xc & ~l1[j], 0));
+        for (int j = 0; j < bw; ++j) { elA |= oa[j].el; elS |= os[j].el; }
+        meta[w] = make_meta((int)(io.raw.size() - off), elS ? 32 - clz32(elS) : 0, elA ? 32 - clz32(elA) : 0, 0, off);
+        for (int j = 0; j < bw; ++j) tight_rotate(ts[j], xn[j]);
+        vprev = vcur; vcur = cw[w + 1].v;
+        ++w; ++steps;
+    }
+    for (int j = 0; j < bw; ++j) {
+        if (!SMALL && tc[j].s) ts[j].lenL = tight_lenL_lookup(tc[j], ts[j], cw, w);
+        tight_leave(ts[j], st[j]);
+        if (w != w_in && cfg[j].s) st[j].xc.idx = w + (cfg[j].s >> 5) + 1;
+    }
+    return steps;
+}
+
 }  // namespace
 
 extern "C" {
@@ -82,7 +150,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
     if (nw == 0) chunks.push_back(Chunk{0, 0, 0, 1});
     for (int w = 0; w < nw; w += chunk_words) chunks.push_back(Chunk{0, w, std::min(nw, w + chunk_words), w + chunk_words >= nw});
 
-    std::vector<std::vector<Meta>> meta(lay.nbands, std::vector<Meta>((size_t)nw + 1, Meta{0u, 0u, 0u, 0u}));
+    std::vector<std::vector<Meta>> meta(lay.nbands, std::vector<Meta>((size_t)nw + 1, Meta{0u, 0u}));
     std::vector<ItemOut> items(chunks.size() * lay.nbands);
     long tight_steps = 0;
 
@@ -136,7 +204,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                         // when every lane's word holds nine failing windows in a row ...
                         bool ok = w >= q + Ha;  // the machines run in this word (not an anchors-only warm-up word)
                         SlowEntry se[32];
-                        for (int j = 0; j < lay.bw; ++j) ok = lane_to_slow(cfg[j], st[j], w, se[j]) && ok;
+                        for (int j = 0; j < lay.bw; ++j) ok = lane_to_slow(cfg[j], st[j], cw, w, se[j]) && ok;
                         if (ok) {
                             for (int j = 0; j < lay.bw; ++j) lane_enter_slow(st[j], se[j]);
                             prev_slow = 1;
@@ -157,48 +225,31 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                         for (int j = 0; j < lay.bw; ++j) if (cfg[j].motif && (st[j].sync & SYNC_ALL) != SYNC_ALL) restart = true;
                     if (restart) break;
                     IterCtx it; it.w = w; it.L = (int)L; it.emit_on = w >= we && w >= e0; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
-                    EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                    EmuSink sk; sk.reset(&io);
                     const uint32_t off = (uint32_t)io.raw.size();
                     for (int j = 0; j < lay.bw; ++j)
                         lane_phase2(sk, cfg[j], st[j], cw, it, j >= 2 ? a[j] : 0u, j >= 1 ? a[j + 1] : 0u,
                                     j + 1 < lay.bw ? a[j + 3] : 0u, j + 2 < lay.bw ? a[j + 4] : 0u, w >= q + Ha);
-                    if (it.emit_on) meta[band][w] = make_meta(sk.counts, sk.dmax[1], sk.dmax[2], it.slow, off);
+                    if (it.emit_on) meta[band][w] = make_meta(sk.nslots, sk.dmax[1], sk.dmax[2], it.slow, off);
                     prev_slow = slow;
                     ++w;
-                    // tight path of the kernel (whole-warp items): consecutive fast, emitting words with the sequential
-                    // phase-1 variant, running plane-word pointers and the fast-word test taken from the loaded words
-                    if (lay.bw == 32 && tight && w > we && w >= e0 && fastrun >= 4 && !prev_slow) {
-                        uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
+                    // tight path of the kernel (scan_tight.h): consecutive fast, emitting words. One item at a time here; the
+                    // kernel couples the items of a warp only in WHEN it enters / leaves the loop and takes the rare paths
+                    if (tight && w > we && w >= e0 && fastrun >= 4 && !prev_slow) {
                         const int wend = std::min(std::min(ch.w1, nw - 1), (((int)L - lay.s_hi) >> 5) - 1);
-                        SeqPtrs sp[32];
-                        for (int j = 0; j < 32; ++j) { sp[j].o = cw + (w + 1); sp[j].b = cw + (w + 1 + (cfg[j].s >> 5) + 1); }
-                        const int w_in = w;
-                        while (w < wend) {
-                            if ((vprev & vcur) != 0xFFFFFFFFu) break;
-                            uint32_t vnext = 0, af[32 + 4] = {0};
-                            for (int j = 0; j < 32; ++j) af[j + 2] = lane_phase1_fast_seq(cfg[j], st[j], cw, w, (int)L, vnext, sp[j], band_m0(lay, band) - 2 <= 15);
-                            IterCtx it2; it2.w = w; it2.L = (int)L; it2.emit_on = 1; it2.slow = 0; it2.prev_slow = 0; it2.fastrun = 4;
-                            EmuSink sk2; sk2.out = &io; sk2.counts = 0u; sk2.dmax[0] = sk2.dmax[1] = sk2.dmax[2] = 0;
-                            const uint32_t off2 = (uint32_t)io.raw.size();
-                            for (int j = 0; j < 32; ++j)
-                                lane_phase2_fast(sk2, cfg[j], st[j], it2, j >= 2 ? af[j] : 0u, j >= 1 ? af[j + 1] : 0u,
-                                                 j + 1 < 32 ? af[j + 3] : 0u, j + 2 < 32 ? af[j + 4] : 0u);
-                            meta[band][w] = make_meta(sk2.counts, sk2.dmax[1], sk2.dmax[2], 0, off2);
-                            vprev = vcur; vcur = vnext;
-                            ++w;
-                            ++tight_steps;
+                        if (w < wend && (cw[w - 1].v & cw[w].v) == 0xFFFFFFFFu) {
+                            const bool small = band_m0(lay, band) - 2 <= 15;
+                            tight_steps += small ? run_tight<true>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band]) : run_tight<false>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band]);
                         }
-                        if (w != w_in)
-                            for (int j = 0; j < 32; ++j) if (cfg[j].s) st[j].xc.idx = w + (cfg[j].s >> 5) + 1;
                     }
                 }
                 if (replay) continue;
                 if (!restart) {
                     if (ch.last) {
-                        EmuSink sk; sk.out = &io; sk.counts = 0u; sk.dmax[0] = sk.dmax[1] = sk.dmax[2] = 0;
+                        EmuSink sk; sk.reset(&io);
                         const uint32_t off = (uint32_t)io.raw.size();
                         for (int j = 0; j < lay.bw; ++j) lane_tail(sk, cfg[j], st[j], (int)L);
-                        meta[band][nw] = make_meta(sk.counts, 0, 0, 1, off);
+                        meta[band][nw] = make_meta(sk.nslots, 0, 0, 1, off);
                     }
                     break;
                 }
@@ -217,14 +268,27 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
         const Chunk ch = chunks[ci];
         const int wend = ch.last ? ch.w1 + 1 : ch.w1;
         for (int w = ch.w0; w < wend; ++w) {
-            std::vector<const Rec*> src(lay.nbands);
-            std::vector<int> cnt(lay.nbands);
+            // merge_count: entries -> kept masks (written back into the slot), stream sizes, elided maxima
+            std::vector<Rec*> slots;
             int tot[3] = {0, 0, 0}, slow = 0, dS = 0, dA = 0;
             for (int b = 0; b < lay.nbands; ++b) {
                 const Meta m = meta[b][w];
-                cnt[b] = meta_total(m);
-                src[b] = items[ci * lay.nbands + b].raw.data() + m.off;
-                for (int s = 0; s < 3; ++s) tot[s] += meta_cnt(m, s);
+                Rec* src = items[ci * lay.nbands + b].raw.data() + m.off;
+                for (int i = 0; i < meta_slots(m); ++i) {
+                    Rec& r = src[i];
+                    const int s = rec_stream(r);
+                    if (rec_is_entry(r)) {
+                        int el;
+                        const uint32_t kept = entry_kept_mask(r, w, cw, el);
+                        r.start = (int32_t)kept;
+                        tot[s] += popc32(kept);
+                        if (s == STREAM_S) dS = std::max(dS, el);
+                        if (s == STREAM_A) dA = std::max(dA, el);
+                    } else {
+                        tot[s] += 1;
+                    }
+                    slots.push_back(&r);
+                }
                 slow |= meta_slow(m);
                 dS = std::max(dS, meta_dmax(m, STREAM_S));
                 dA = std::max(dA, meta_dmax(m, STREAM_A));
@@ -236,12 +300,28 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                 if (ps) { res[s].push_back(pseudo_rec(w, emax[s - 1] - 1)); base[s] += 1; }
                 res[s].resize(base[s] + tot[s]);
             }
-            for (int b = 0; b < lay.nbands; ++b)
-                for (int i = 0; i < cnt[b]; ++i) {
-                    const Rec r = src[b][i];
-                    const int s = (r.mflags >> REC_STREAM_SHIFT) & 3;
-                    res[s][base[s] + rank_in_bucket(r, src.data(), cnt.data(), lay.nbands)] = finalize_rec(r, w);
+            // merge_write: every candidate ranks itself among the candidates of its stream in the bucket
+            for (Rec* rp : slots) {
+                const Rec r = *rp;
+                const int s = rec_stream(r);
+                auto rank_of = [&](uint32_t key) {
+                    int rank = 0;
+                    for (Rec* op : slots) if (rec_stream(*op) == s) rank += slot_count_below(*op, key);
+                    return rank;
+                };
+                if (!rec_is_entry(r)) {
+                    res[s][base[s] + rank_of((uint32_t)r.key)] = finalize_rec(r, w);
+                    continue;
                 }
+                for (uint32_t x = (uint32_t)r.start; x; x &= x - 1u) {
+                    const int i = ctz32(x);
+                    Rec o;
+                    entry_interval(r, w, cw, i, o.start, o.end);
+                    o.mflags = rec_mlen(r);
+                    o.key = 32 * w + i;
+                    res[s][base[s] + rank_of(entry_key(i, rec_mlen(r)))] = o;
+                }
+            }
             emax[0] = std::max<long long>(emax[0], elided_end_code(w, dS));
             emax[1] = std::max<long long>(emax[1], elided_end_code(w, dA));
         }
