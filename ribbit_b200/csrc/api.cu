@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,8 +48,8 @@ struct rb_ctx {
     bool ascii_external = false;
     const void* ascii_dev_ext = nullptr;
 
-    DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_chunks, d_item_base, d_item_cap, d_item_count,
-        d_meta, d_bsum, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys, d_text, d_ftiles, d_finfo, d_ftot, d_hpos, d_hseq;
+    DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_nmask, d_chunks, d_item_base, d_item_cap, d_item_count,
+        d_meta, d_bsum, d_item_clk, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys, d_text, d_ftiles, d_finfo, d_ftot, d_hpos, d_hseq;
     DevBatch batch{};
 
     // pinned host results
@@ -129,8 +130,10 @@ void make_chunks(rb_ctx* c, long long total_words, int range_first, int range_la
     const BandLayout& lay = c->lay;
     int cw = c->params.chunk_words;
     if (cw <= 0) {
-        const long long target_chunks = std::max<long long>(1, 148ll * 64 / lay.nbands);
-        cw = (int)std::min<long long>(1 << 20, std::max<long long>(64, (total_words + target_chunks - 1) / target_chunks));
+        // one-warp items (chunk x band), 16 resident per SM: about 32 waves of them keep the tail short; chunks of at least
+        // 256 words amortise the warm-up in front of every chunk, longer ones are not needed for that
+        const long long target_items = 148ll * 16 * 32;
+        cw = (int)std::min<long long>(8192, std::max<long long>(256, total_words * lay.nbands / target_items));
     }
     c->chunks.clear();
     const int n = (int)c->contigs.size();
@@ -229,6 +232,7 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.n_active = b.n_buckets;
     b.n_plane_words = c->plane_start[n];
     b.warm0 = WARMUP_WORDS;
+    if (const char* e = getenv("RB_WARM0")) b.warm0 = std::max(1, atoi(e));  // diagnostics
     b.debug = c->params.reserved;
     b.n_merge_blocks = (int)((b.n_buckets + MERGE_BLOCK - 1) / MERGE_BLOCK);
     if ((rc = ensure(c, c->d_planes, (size_t)b.n_plane_words * sizeof(PlaneWord)))) return rc;
@@ -243,6 +247,8 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.plane_start = (const long long*)c->d_plane_start.p;
     b.bucket_base = (const long long*)c->d_bucket_base.p;
     b.planes = (PlaneWord*)c->d_planes.p;
+    if ((rc = ensure(c, c->d_nmask, (size_t)((b.n_plane_words + 31) / 32 + 1) * sizeof(uint32_t)))) return rc;
+    b.nmask = (uint32_t*)c->d_nmask.p;
     b.chunks = (const Chunk*)c->d_chunks.p;
     b.meta = (Meta*)c->d_meta.p;
     b.bsum = (BucketSum*)c->d_bsum.p;
@@ -296,8 +302,8 @@ void rb_destroy(rb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_chunks,
-                      &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_bsum, &c->d_raw, &c->d_counters,
+    DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_nmask, &c->d_chunks,
+                      &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_bsum, &c->d_item_clk, &c->d_raw, &c->d_counters,
                       &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long, &c->d_mitems, &c->d_mkeys,
                       &c->d_text, &c->d_ftiles, &c->d_finfo, &c->d_ftot, &c->d_hpos, &c->d_hseq};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -514,6 +520,25 @@ int rb_scan_device(rb_ctx* c) {
     RB_CUDA(c, cudaEventElapsedTime(&tm.total_ms, c->ev[0], c->ev[3]));
     c->timing = tm;
     c->scanned = true;
+    return RB_OK;
+}
+
+/* diagnostics: per (chunk, band) item of the last scan {start, end} in GPU globaltimer nanoseconds; the first call only
+ * switches the recording on (returns RB_E_STATE), later calls after a scan return the n_items pairs */
+int rb_debug_item_clocks(rb_ctx* c, int64_t* out, int64_t capacity_items, int64_t* n_items) {
+    if (!c || !n_items) return RB_E_ARG;
+    RB_CUDA(c, cudaSetDevice(c->device));
+    const long long n = c->batch.n_items;
+    *n_items = n;
+    if (!c->batch.item_clk) {
+        int rc = ensure(c, c->d_item_clk, (size_t)std::max<long long>(n, 1) * 4 * sizeof(long long));
+        if (rc) return rc;
+        RB_CUDA(c, cudaMemset(c->d_item_clk.p, 0, (size_t)std::max<long long>(n, 1) * 4 * sizeof(long long)));
+        c->batch.item_clk = (long long*)c->d_item_clk.p;
+        return fail(c, RB_E_STATE, "rb_debug_item_clocks: recording switched on; scan again");
+    }
+    if (!out || capacity_items < n) return fail(c, RB_E_ARG, "rb_debug_item_clocks: capacity");
+    RB_CUDA(c, cudaMemcpy(out, c->d_item_clk.p, (size_t)n * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
     return RB_OK;
 }
 

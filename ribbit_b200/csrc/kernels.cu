@@ -24,7 +24,12 @@ __device__ __forceinline__ int find_segment(const long long* __restrict__ starts
 
 __global__ void __launch_bounds__(256) pack_kernel(DevBatch b) {
     const long long pw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pw >= b.n_plane_words) return;
+    const bool valid = pw < b.n_plane_words;
+    if (!valid) {  // the warp still votes below
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, false);
+        if ((threadIdx.x & 31) == 0 && (pw >> 5) < ((b.n_plane_words + 31) >> 5)) b.nmask[pw >> 5] = m;
+        return;
+    }
     const int c = find_segment(b.plane_start, b.n_contigs, pw);
     const Contig cg = b.contigs[c];
     const long long w = pw - b.plane_start[c] - 1;  // word of the contig, -1 and >= nw are guard words
@@ -79,6 +84,9 @@ __global__ void __launch_bounds__(256) pack_kernel(DevBatch b) {
         o.v = ~(uint32_t)t;
     }
     b.planes[pw] = o;
+    // one bit per plane word: all 32 positions are N (or padding); the scan's N-run probe reads 32 words per load
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, o.n == 0xFFFFFFFFu);
+    if ((threadIdx.x & 31) == 0) b.nmask[pw >> 5] = m;
 }
 
 void launch_pack(const DevBatch& b, cudaStream_t st) {
@@ -144,97 +152,175 @@ struct TightIO {
     uint32_t cap_end;  // first index past the item's reservation
     int w, wend, L;
     int on;            // the group takes part (0: finished or warming up; its lanes only keep the warp converged)
+    unsigned lt;       // lanes below this one (read back from memory so that it is not rematerialised from S2R per use)
 };
 
-template <int BW, bool SMALL>
-__device__ __noinline__ void tight_run(TightIO* io) {
+// rare path of the tight loop, out of line: keeps the loop body small (instruction cache) and its registers free
+template <int TIER>
+__device__ __noinline__ uint32_t tight_rare(const TightCfg& c, TightState& t, const PlaneWord* cw, int w, int L, uint32_t xn, uint32_t a,
+                                            int lenL0, bool prev_rare) {
+    bool full;
+    a = tight_anchor_rare<TIER>(c, t, cw, w, L, xn, a, lenL0, prev_rare, full);
+    if (__any_sync(0xFFFFFFFFu, full)) {
+        if (full) a = tight_anchor_full(c, t, cw, w, L, xn);
+    }
+    return a;
+}
+
+// everything the loop carries besides the per-word lane state
+struct TightLoop {
+    TightCfg c;
+    const PlaneWord* cw;
+    Rec* raw;
+    const uint4* po;   // plane word w + 1 (all lanes)
+    const uint2* pb;   // h / l of plane word w + 1 + (s >> 5) + 1 (per lane)
+    Meta* mp;          // bucket metadata of word w
+    uint32_t off, cap_end;
+    int w, wend, L;
+    uint32_t vprev, vcur;
+    uint4 o;           // plane word w + 1 and
+    uint2 bb;          //   the lane's b operand, loaded one step ahead
+    unsigned lt;
+    int flags;         // bit 0 / 1: a lane flagged word w / w - 1 (TF_SUSC, TF_SUSP); bit 2: the previous word took the rare path
+    bool on;
+    int zc;
+};
+enum : int { TF_SUSC = 1, TF_SUSP = 2, TF_PREV_RARE = 4 };
+
+template <int BW, int TIER>
+__device__ __forceinline__ bool tight_leave_now(const TightLoop& q) {
+    const bool go = !q.on || (q.w < q.wend && (q.vprev & q.vcur) == 0xFFFFFFFFu);
+    if (BW == 32) return !go;
+    // every group that takes part must have a fast word in front of it, else the warp leaves the loop
+    return !__all_sync(0xFFFFFFFFu, go) || !__any_sync(0xFFFFFFFFu, q.on);
+}
+
+template <int TIER>
+__device__ __forceinline__ void tight_finish(TightIO* io, const TightLoop& q, TightState t) {
+    if (TIER != TIER_SMALL && q.c.s && q.on && !(q.flags & TF_PREV_RARE)) t.lenL = tight_lenL_lookup(q.c, t, q.cw, q.w);  // the general path carries the run length
+    io->t = t;
+    io->off = q.off;
+    io->w = q.w;
+}
+
+// one word: state `in` (word w-1 rotated in) -> state `out`
+template <int BW, int TIER>
+__device__ __forceinline__ void tight_step(TightLoop& q, const TightState& in, TightState& t) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    const int g = lane / BW, j = lane % BW;
-    const unsigned gmask = (BW == 32) ? FULL : (((1u << BW) - 1u) << (g * BW));
-    const unsigned lt = (1u << lane) - 1u;
-    TightState t = io->t;
-    const TightCfg c = io->c;
-    const PlaneWord* __restrict__ cw = io->cw;
-    Rec* __restrict__ raw = io->raw;
-    uint32_t off = io->off;
-    const uint32_t cap_end = io->cap_end;
-    int w = io->w;
-    const int wend = io->wend, L = io->L;
-    const bool on = io->on != 0;
-    const uint4* po = reinterpret_cast<const uint4*>(cw + (w + 1));
-    const uint2* pb = reinterpret_cast<const uint2*>(cw + (w + 1 + (c.s >> 5) + 1));
-    Meta* mp = io->meta + w;
-    uint32_t vprev = on ? cw[w - 1].v : FULL, vcur = on ? cw[w].v : FULL;
-    bool susp = true, susc = true;  // !SMALL: nothing is known about the two words in front: the first steps take the exact anchors
-    int zc = 0;                     // consecutive words without a passing substitution window in any lane (saturating)
-    for (;;) {
-        // every group that takes part must have a fast word in front of it, else the warp leaves the loop
-        const bool go = !on || (w < wend && (vprev & vcur) == FULL);
-        if (!__all_sync(FULL, go) || !__any_sync(FULL, on)) break;
-        const uint4 o = __ldg(po);
-        const uint2 bb = __ldg(pb);
-        ++po; pb += 2;
-        uint32_t xn, l1;
-        bool sus;
-        const int lenL0 = t.lenL;
-        uint32_t a = tight_phaseA<SMALL>(c, t, o.x, o.y, bb.x, bb.y, xn, l1, sus);
-        bool rare = __any_sync(FULL, sus);
-        if (!SMALL) {
-            const bool r3 = rare | susc | susp;
-            susp = susc; susc = rare; rare = r3;
-        }
-        if (rare) a = tight_anchor_exact<SMALL>(c, t, cw, w, L, xn, lenL0);
-        const uint32_t pair = a | __shfl_down_sync(FULL, a, 1);
-        const uint32_t an = __shfl_up_sync(FULL, pair, 2) | __shfl_down_sync(FULL, pair, 1);
-        uint32_t passS, passA, cand;
-        tight_windows(c, t, an, l1, passS, passA, cand);
-        const int p0 = 32 * w;
-        TightOut oa, os;
-        tight_events_A<SMALL>(c, t, p0, passA, oa);
+    constexpr bool WHOLE = BW == 32;  // one item per warp: everything about the item is warp-uniform
+    const unsigned gmask = WHOLE ? FULL : (((1u << BW) - 1u) << (((threadIdx.x & 31) / BW) * BW));
+    const unsigned lt = q.lt;
+    const TightCfg& c = q.c;
+    t = in;
+    const uint4 o = q.o;
+    const uint2 bb = q.bb;
+    const int adv = (WHOLE || q.on) ? 1 : 0;  // lanes of a group that sits out keep reading the same (valid) words
+    q.po += adv; q.pb += 2 * adv;
+    q.o = __ldg(q.po);   // for the next step (always readable: guard words follow every contig)
+    q.bb = __ldg(q.pb);
+    uint32_t xn, l1;
+    bool sus;
+    const int lenL0 = t.lenL;
+    uint32_t a = tight_phaseA<TIER>(c, t, o.x, o.y, bb.x, bb.y, xn, l1, sus);
+    const bool any_sus = __any_sync(FULL, sus);
+    bool rare = any_sus;
+    if (TIER != TIER_SMALL) rare = any_sus || (q.flags & (TF_SUSC | TF_SUSP)) != 0;
+    if (rare) {
+        // only xp, xc and lenL of the state are touched: pass a small copy, not the whole TightState
+        TightState tr;
+        tr.xp = t.xp; tr.xc = t.xc; tr.lenL = t.lenL;
+        a = tight_rare<TIER>(c, tr, q.cw, q.w, q.L, xn, a, lenL0, (q.flags & TF_PREV_RARE) != 0);
+        t.lenL = tr.lenL;
+    }
+    q.flags = ((q.flags & TF_SUSC) << 1) | (any_sus ? TF_SUSC : 0) | (rare ? TF_PREV_RARE : 0);
+    const uint32_t pair = a | __shfl_down_sync(FULL, a, 1);
+    const uint32_t an = __shfl_up_sync(FULL, pair, 2) | __shfl_down_sync(FULL, pair, 1);
+    uint32_t passS, passA, cand;
+    tight_windows(c, t, an, l1, passS, passA, cand);
+    const int p0 = 32 * q.w;
+    TightOut oa, os;
+    tight_events_A<TIER>(c, t, p0, passA, oa);
+    const uint32_t elA = __reduce_or_sync(gmask, oa.el);
+    cand &= c.mmask;
+    // mask entries: one slot per (lane, stream) with surviving candidates, packed by ballot
+    const uint32_t off_in = q.off;
+    uint32_t off = q.off;
+    const bool on = WHOLE ? true : q.on;
+    const bool hA = on && oa.x != 0u;
+    const unsigned balA = __ballot_sync(FULL, hA);
+    const bool anyPS = __any_sync(FULL, (cand | passS) != 0u);
+    if (balA) {
+        const unsigned mine = balA & gmask;
+        const uint32_t pos = off + __popc(mine & lt);
+        if (hA && pos < q.cap_end) *reinterpret_cast<int4*>(q.raw + pos) = make_int4((int)oa.x, (int)oa.s, c.s | (REC_ENTRY << 16) | (STREAM_A << REC_STREAM_SHIFT), oa.last);
+        off += __popc(mine);
+    }
+    uint32_t elS = 0u;
+    // perfect and substitution candidates are rare: one vote covers both
+    if (anyPS || q.zc < 2) {
+        const bool hP = on && cand != 0u;
+        const unsigned balP = __ballot_sync(FULL, hP);
         const bool actS = __any_sync(FULL, passS != 0u);
-        os.x = 0u; os.s = 0u; os.el = 0u; os.last = 0;
-        if (actS || zc < 2) {
-            tight_events_S(t, p0, passS, os);
-            zc = actS ? 0 : zc + 1;
-        }
-        cand &= c.mmask;
-        // mask entries: one slot per (lane, stream) with surviving candidates, packed by ballot
-        const uint32_t off_in = off;
-        const bool hA = on && oa.x != 0u;
-        const unsigned balA = __ballot_sync(FULL, hA);
-        if (balA) {
-            const unsigned mine = balA & gmask;
+        if (balP) {
+            const unsigned mine = balP & gmask;
             const uint32_t pos = off + __popc(mine & lt);
-            if (hA && pos < cap_end) *reinterpret_cast<int4*>(raw + pos) = make_int4((int)oa.x, (int)oa.s, c.s | (REC_ENTRY << 16) | (STREAM_A << REC_STREAM_SHIFT), oa.last);
+            if (hP && pos < q.cap_end) *reinterpret_cast<int4*>(q.raw + pos) = make_int4((int)cand, (int)(t.xc & ~l1), c.s | (REC_ENTRY << 16) | (STREAM_P << REC_STREAM_SHIFT), 0);
             off += __popc(mine);
         }
-        const bool hS = on && os.x != 0u, hP = on && cand != 0u;
-        if (__any_sync(FULL, hS | hP)) {
-            const unsigned mS = __ballot_sync(FULL, hS) & gmask, mP = __ballot_sync(FULL, hP) & gmask;
-            const uint32_t posS = off + __popc(mS & lt);
-            if (hS && posS < cap_end) *reinterpret_cast<int4*>(raw + posS) = make_int4((int)os.x, (int)os.s, c.s | (REC_ENTRY << 16) | (STREAM_S << REC_STREAM_SHIFT), os.last);
-            off += __popc(mS);
-            const uint32_t posP = off + __popc(mP & lt);
-            if (hP && posP < cap_end) *reinterpret_cast<int4*>(raw + posP) = make_int4((int)cand, (int)(t.xc & ~l1), c.s | (REC_ENTRY << 16) | (STREAM_P << REC_STREAM_SHIFT), 0);
-            off += __popc(mP);
+        tight_events_S(t, p0, passS, os);
+        q.zc = actS ? 0 : q.zc + 1;
+        const bool hS = on && os.x != 0u;
+        const unsigned balS = __ballot_sync(FULL, hS);
+        elS = __reduce_or_sync(gmask, os.el);
+        if (balS) {
+            const unsigned mine = balS & gmask;
+            const uint32_t pos = off + __popc(mine & lt);
+            if (hS && pos < q.cap_end) *reinterpret_cast<int4*>(q.raw + pos) = make_int4((int)os.x, (int)os.s, c.s | (REC_ENTRY << 16) | (STREAM_S << REC_STREAM_SHIFT), os.last);
+            off += __popc(mine);
         }
-        const uint32_t elA = __reduce_or_sync(gmask, oa.el), elS = __reduce_or_sync(gmask, os.el);
-        if (j == 0 && on) *mp = make_meta((int)(off - off_in), 32 - __clz((int)elS), 32 - __clz((int)elA), 0, off_in);
-        ++mp;
-        tight_rotate(t, xn);
-        vprev = vcur; vcur = o.w;
-        ++w;
     }
-    if (!SMALL && c.s && on) t.lenL = tight_lenL_lookup(c, t, cw, w);  // the general path carries the run length
-    io->t = t;
-    io->off = off;
-    io->w = w;
+    // every lane of the item stores the same word to the same address
+    if (on) *q.mp = make_meta((int)(off - off_in), 32 - __clz((int)elS), 32 - __clz((int)elA), 0, off_in);
+    q.off = off;
+    ++q.mp;
+    tight_rotate(t, xn);
+    q.vprev = q.vcur; q.vcur = o.w;
+    ++q.w;
+}
+
+template <int BW, int TIER>
+__device__ __noinline__ void tight_run(TightIO* io) {
+    TightLoop q;
+    q.c = io->c;
+    q.cw = io->cw; q.raw = io->raw;
+    q.off = io->off; q.cap_end = io->cap_end;
+    q.w = io->w; q.wend = io->wend; q.L = io->L;
+    q.on = BW == 32 ? true : io->on != 0;
+    q.po = reinterpret_cast<const uint4*>(q.cw + (q.w + 1));
+    q.pb = reinterpret_cast<const uint2*>(q.cw + (q.w + 1 + (q.c.s >> 5) + 1));
+    q.mp = io->meta + q.w;
+    q.vprev = q.on ? q.cw[q.w - 1].v : 0xFFFFFFFFu; q.vcur = q.on ? q.cw[q.w].v : 0xFFFFFFFFu;
+    // flags of the two words in front: unknown, so the first steps take the exact anchors; t.lenL is the general path's
+    // carried run length
+    q.flags = TF_SUSC | TF_SUSP | TF_PREV_RARE;
+    q.lt = io->lt;
+    q.o = __ldg(q.po); q.bb = __ldg(q.pb);
+    q.zc = 0;                      // consecutive words without a passing substitution window in any lane (saturating)
+    TightState ta = io->t, tb;
+    // two words per trip with the roles of the two state objects swapped: the carried words of a step are born in other
+    // registers than the ones they replace, so no register moves are needed at the loop end
+#pragma unroll 1
+    for (;;) {
+        if (tight_leave_now<BW, TIER>(q)) { tight_finish<TIER>(io, q, ta); return; }
+        tight_step<BW, TIER>(q, ta, tb);
+        if (tight_leave_now<BW, TIER>(q)) { tight_finish<TIER>(io, q, tb); return; }
+        tight_step<BW, TIER>(q, tb, ta);
+    }
 }
 
 template <int BW>
 #ifndef RB_SCAN_BLOCKS_PER_SM
-#define RB_SCAN_BLOCKS_PER_SM 20
+#define RB_SCAN_BLOCKS_PER_SM 16
 #endif
 __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_kernel(DevBatch b) {
     constexpr int GROUPS = 32 / BW;
@@ -242,9 +328,18 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / BW, j = lane % BW;
     const unsigned gmask = (BW == 32) ? 0xFFFFFFFFu : (((1u << BW) - 1u) << (g * BW));
-    const long long item = ((long long)blockIdx.x * SCAN_WARPS + warp) * GROUPS + g;
-    bool active = item < b.n_items;
+    // launch order: band-major (all chunks of band 0, then band 1, ...), so that the warps resident on an SM run the same
+    // variant of the tight loop most of the time (instruction cache) and the costliest band (small shifts) starts first;
+    // the item tables are chunk-major (item = chunk * nbands + band)
     const int nbands = b.lay.nbands;
+    const long long slot = ((long long)blockIdx.x * SCAN_WARPS + warp) * GROUPS + g;
+    const long long item = nbands == 1 ? slot : (slot % b.n_chunks) * nbands + slot / b.n_chunks;
+    bool active = slot < b.n_items;
+    if (b.item_clk && active && j == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        b.item_clk[4 * item] = (long long)t0;
+    }
     const int band = active ? (int)(item % nbands) : 0;
     Chunk ch;
     ch.contig = 0; ch.w0 = 0; ch.w1 = 0; ch.last = 0;
@@ -263,26 +358,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     sk.cnt = cnt;
     const uint32_t off0 = active ? (uint32_t)b.item_base[item] : 0u;
 
-    // first word of the run of full-N words that ends right before the chunk (group-parallel backward probe)
-    int nb = ch.w0;
-    {
-        bool go = active && ch.w0 > 0;
-        while (__any_sync(0xFFFFFFFFu, go)) {
-            const int wq = nb - 1 - j;
-            const bool f = go && wq >= 0 && full_n(cw, wq);
-            const unsigned bits = (__ballot_sync(0xFFFFFFFFu, f) & gmask) >> (g * BW);
-            const unsigned inv = ~bits & (BW == 32 ? 0xFFFFFFFFu : ((1u << BW) - 1u));
-            const int c = inv ? __ffs((int)inv) - 1 : BW;
-            if (go) {
-                nb -= c;
-                if (c < BW || nb <= 0) go = false;
-            }
-        }
-    }
     // a chunk that lies strictly inside an N run (the word before it and all its words are N) emits nothing:
     // no window is evaluated and every run was closed by the first N of the run
     {
-        bool alln = active && nb < ch.w0 && !ch.last && !(b.debug & 2);
+        bool alln = active && ch.w0 > 0 && full_n(cw, ch.w0 - 1) && !ch.last && !(b.debug & 2);
         for (int base = 0; __any_sync(0xFFFFFFFFu, alln && ch.w0 + base < ch.w1); base += BW) {  // warp-uniform trip count
             const int wq = ch.w0 + base + j;
             const bool f = !alln || wq >= ch.w1 || full_n(cw, wq);
@@ -294,6 +373,38 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             if (j == 0) b.item_count[item] = 0;
             active = false;
         }
+    }
+    // first word of the run of full-N words that ends right before the chunk: backward probe over the full-N bit mask of
+    // the plane words (pack_kernel), 32 words per load, one load per lane and trip
+    int nb = ch.w0;
+    {
+        bool go = active && ch.w0 > 0 && full_n(cw, ch.w0 - 1);
+        long long p = cg.word_base + ch.w0 - 1;  // plane index of the word in front of the chunk
+        if (go) {
+            // the mask word that holds p: the ones at and below bit (p & 31)
+            const int bit = (int)(p & 31);
+            const uint32_t z = ~b.nmask[p >> 5] & lowmask(bit + 1);
+            const int k = z ? bit - (31 - __clz((int)z)) : bit + 1;
+            nb -= k; p -= k;
+            if (z) go = false;
+        }
+        while (__any_sync(0xFFFFFFFFu, go)) {
+            // p is the last word of a mask word now; lane j looks at the j-th mask word further back
+            const long long gq = (p >> 5) - j;
+            const uint32_t m = (go && gq >= 0) ? b.nmask[gq] : 0u;
+            const unsigned bits = (__ballot_sync(0xFFFFFFFFu, m == 0xFFFFFFFFu) & gmask) >> (g * BW);
+            const unsigned inv = ~bits & (BW == 32 ? 0xFFFFFFFFu : ((1u << BW) - 1u));
+            const int c = inv ? __ffs((int)inv) - 1 : BW;  // mask words that are all ones
+            const uint32_t mc = __shfl_sync(0xFFFFFFFFu, m, (g * BW + min(c, BW - 1)) & 31);  // the first one that is not
+            if (go) {
+                nb -= 32 * c; p -= 32ll * c;
+                if (c < BW) {
+                    nb -= __clz((int)~mc);  // its ones from the top
+                    go = false;
+                }
+            }
+        }
+        if (nb < 0) nb = 0;  // the guard word in front of the contig is N as well
     }
     const int nb0 = nb;
     LaneState st;
@@ -310,6 +421,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     if (j == 0) *cnt = 0;
     __syncwarp();
     int restarts = 0;
+    int dbg_gen = 0, dbg_slow = 0;  // diagnostics: words through the general path / of them bit-serial
     if (active && ch.w0 >= ch.w1) {  // empty contig: only the tail bucket
         active = false;
         if (ch.last) {
@@ -319,7 +431,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     }
 
     const int guard = b.lay.guard;
-    const bool small_band = band_m0(b.lay, band) - 2 <= 15;  // the item holds shifts <= 15 (uniform over the warp: see launch_scan)
+    const int tier = tight_tier(band_m0(b.lay, band) - 2);  // by the item's smallest shift; uniform over the warp (see launch_scan)
     // The neighbour anchors of lanes at the edge of an item need no masking: lanes 0 and 1 of an item are halo
     // shifts (never motif lanes) and a motif lane has j + 2 <= mpb + 3 < BW (layout.h), so every value a motif lane
     // reads comes from its own item.
@@ -336,6 +448,13 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             __syncwarp(gmask);
             if (j == 0) {
                 const int n = *cnt;
+                if (b.item_clk) {
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    b.item_clk[4 * item + 1] = (long long)t1;
+                    b.item_clk[4 * item + 2] = dbg_gen;
+                    b.item_clk[4 * item + 3] = ((long long)restarts << 32) | (unsigned)dbg_slow;
+                }
                 b.item_count[item] = n;
                 if (n > sk.cap) atomicAdd(b.counters + 0, 1);
                 if (restarts) atomicAdd(b.counters + 1, restarts);
@@ -429,6 +548,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             }
             prev_slow = slow;
             ++w;
+            ++dbg_gen; dbg_slow += slow;
         }
 
         // ---- tight path: consecutive fast, emitting words ------------------------------------------------------------
@@ -444,7 +564,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             io.c = make_tight_cfg(cfg);
             io.cw = cw; io.meta = meta; io.raw = b.raw; io.off = off; io.cap_end = off0 + (uint32_t)sk.cap;
             io.w = w; io.wend = wend; io.L = L; io.on = want ? 1 : 0;
-            if (small_band) tight_run<BW, true>(&io); else tight_run<BW, false>(&io);
+            io.lt = (1u << lane) - 1u;
+            if (tier == TIER_SMALL) tight_run<BW, TIER_SMALL>(&io);
+            else if (tier == TIER_MID) tight_run<BW, TIER_MID>(&io);
+            else tight_run<BW, TIER_LARGE>(&io);
             if (want) {
                 tight_leave(io.t, st);
                 if (io.w != w && cfg.s) st.xc.idx = io.w + (cfg.s >> 5) + 1;  // the cached plane word: the last b operand

@@ -39,6 +39,7 @@ struct DevBatch {
     const long long* plane_start;   // [n_contigs + 1] first plane word (the guard word in front) of each contig
     const long long* bucket_base;   // [n_contigs + 1]
     PlaneWord* planes;
+    uint32_t* nmask;                // [ceil(n_plane_words / 32)] bit i of word g: plane word 32 g + i is all N / padding
     const Chunk* chunks;            // [n_chunks]
     const long long* item_base;     // [n_items] first raw record of the item
     const int* item_cap;            // [n_items]
@@ -46,6 +47,7 @@ struct DevBatch {
     Meta* meta;                     // [nbands][n_buckets]
     BucketSum* bsum;                // [n_buckets]
     Rec* raw;                       // raw slot pool
+    long long* item_clk;            // diagnostics (rb_debug_item_clocks): [n_items][2] start / end of the item in globaltimer ns, or null
     int* counters;                  // [0] overflowed items, [1] warm-up restarts, [2] a count field overflowed (error)
     // merge
     BlockPartial* partial;          // [n_merge_blocks + 1]; after M2: exclusive prefixes, last = totals

@@ -73,10 +73,18 @@ RB_HD void tight_leave(const TightState& t, LaneState& st) {
 }
 
 // ---- phase A: X_s[w+1] and the anchor word A_s[w] ---------------------------------------------------------------------
+// Items come in three kinds by their smallest shift s_min (uniform over a warp):
+//   TIER_SMALL (s_min <= 15)  runs inside a word can reach 2s: exact edge logic and in-word doubling in every step
+//   TIER_MID   (s_min <= 47)  a run of >= 2s >= 32 positions that touches word w covers an aligned half word of w-1, w
+//                             or w+1: the straight-line anchors are exact unless some lane sees such a half word
+//   TIER_LARGE (s_min >= 48)  2s >= 96: such a run covers all of word w-1, w or w+1
+// When a lane of the item raises its flag the item takes tight_anchor_rare for that word.
+enum : int { TIER_SMALL = 0, TIER_MID = 1, TIER_LARGE = 2 };
+RB_HD int tight_tier(int s_min) { return s_min <= 15 ? TIER_SMALL : (s_min <= 47 ? TIER_MID : TIER_LARGE); }
+
 // oh / ol = h / l of plane word w+1 (the same for every lane), bh / bl = h / l of plane word w + 1 + (s >> 5) + 1.
-// Returns the straight-line anchor word; `sus` tells that some run touching the word may reach 2s positions (or that the
-// word / its successor is all ones), in which case the item recomputes the word with tight_anchor_exact.
-template <bool SMALL>
+// Returns the straight-line anchor word; `sus` = this lane's flag for word w+1 (SMALL: for words w, w+1).
+template <int TIER>
 RB_HD uint32_t tight_phaseA(const TightCfg& c, TightState& t, uint32_t oh, uint32_t ol, uint32_t bh, uint32_t bl, uint32_t& xn,
                             uint32_t& l1, bool& sus) {
     xn = ~((oh ^ fsr(t.bh, bh, c.sh)) | (ol ^ fsr(t.bl, bl, c.sh)));
@@ -86,14 +94,16 @@ RB_HD uint32_t tight_phaseA(const TightCfg& c, TightState& t, uint32_t oh, uint3
     const uint32_t l2 = fsl(t.xp, x, 2), r1 = fsr(x, xn, 1), r2 = fsr(x, xn, 2);
     // positions of X_s that lie in a run of at least 3 (anchor_size, parse_anchored_shiftxor.cpp:44)
     uint32_t a = x & ((l1 & (l2 | r1)) | (r1 & r2)) & c.amask;
-    if (!SMALL) {
-        // 2s >= 50 here: a run of that length touching word w covers an aligned half word of w-1, w or w+1; the caller
-        // keeps the flags of the two previous words
-        const uint32_t u = ~xn;
-        sus = (((u - 0x00010001u) & xn & 0x80008000u) != 0u);
+    if (TIER == TIER_LARGE) {
+        sus = c.s != 0 && xn == 0xFFFFFFFFu;
         return a;
     }
-    sus = (x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu);
+    if (TIER == TIER_MID) {
+        const uint32_t u = ~xn;
+        sus = c.s != 0 && (((u - 0x00010001u) & xn & 0x80008000u) != 0u);  // a half word of xn is all ones
+        return a;
+    }
+    sus = c.s != 0 && ((x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu));  // idle lanes (shift 0: all ones) never raise it
     // runs that touch a word edge: their full length is known from the neighbours
     const int lead = ctz32(~x), trail = clz32(~x), leadn = ctz32(~xn);
     a &= (t.lenL + lead >= c.K2) ? ~lowmask(lead) : 0xFFFFFFFFu;
@@ -107,12 +117,12 @@ RB_HD uint32_t tight_phaseA(const TightCfg& c, TightState& t, uint32_t oh, uint3
         for (int k = 1; k < c.K2;) { const int sh = (k < c.K2 - k) ? k : c.K2 - k; d |= d << sh; k += sh; }
         a &= ~d;
     }
-    t.lenL = trail;  // meaningless when sus: tight_anchor_exact sets it
+    t.lenL = trail;  // meaningless when sus: tight_anchor_rare sets it
     return a;
 }
 
 // Length of the run of ones of X_s that ends at the end of word w-1 (t.xp = X_s[w-1]), looked up in the planes when that
-// word is all ones; saturates above K2 + 32. Used where the run length is not carried (items without small shifts).
+// word is all ones; saturates above K2 + 32. Used when the loop is left (items that do not carry the run length).
 RB_HD int tight_lenL_lookup(const TightCfg& c, const TightState& t, const PlaneWord* cw, int w) {
     int lenL = clz32(~t.xp);
     if (lenL == 32)
@@ -124,15 +134,30 @@ RB_HD int tight_lenL_lookup(const TightCfg& c, const TightState& t, const PlaneW
     return lenL;
 }
 
-// Exact anchor word for a word tight_phaseA flagged (any lane of the item): the general anchor_word with the run length in
-// front of the word looked up in the planes when the previous word is all ones.
-template <bool SMALL>
-RB_HD uint32_t tight_anchor_exact(const TightCfg& c, TightState& t, const PlaneWord* cw, int w, int L, uint32_t xn, int lenL_in) {
-    if (!c.s) return 0u;
-    int lenL = SMALL ? lenL_in : tight_lenL_lookup(c, t, cw, w);
-    const uint32_t a = anchor_word(cw, w, L, c.s, t.xc, xn, lenL);
-    t.lenL = lenL;
+// Exact anchor word for a word some lane of the item flagged. a = the straight-line result of tight_phaseA, lenL_in =
+// t.lenL before that call, prev_rare = the previous word took this path too (then t.lenL is the carried run length; if
+// not, the previous word raised no flag, so X_s[w-1] has no all-ones (half) word and its trailing ones are the run).
+// MID / LARGE: while neither this word nor the next is all ones the runs that touch an edge of the word are judged with
+// their known lengths; whole words of ones take the general anchor_word.
+template <int TIER>
+RB_HD uint32_t tight_anchor_rare(const TightCfg& c, TightState& t, const PlaneWord* cw, int w, int L, uint32_t xn, uint32_t a,
+                                 int lenL_in, bool prev_rare, bool& full) {
+    const uint32_t x = t.xc;
+    full = c.s != 0 && ((x == 0xFFFFFFFFu) | (xn == 0xFFFFFFFFu));
+    if (TIER == TIER_SMALL) {
+        if (full) t.lenL = lenL_in;  // tight_phaseA left the trailing ones of the word there
+        return a;
+    }
+    const int lenL = prev_rare ? lenL_in : clz32(~t.xp);
+    const int lead = ctz32(~x), trail = clz32(~x), leadn = ctz32(~xn);
+    a &= (lenL + lead >= c.K2) ? ~lowmask(lead) : 0xFFFFFFFFu;
+    a &= (trail + leadn >= c.K2) ? lowmask(32 - trail) : 0xFFFFFFFFu;
+    t.lenL = full ? lenL : trail;
     return a;
+}
+// second half of the rare path, for the lanes with `full`: t.lenL holds the run length in front of the word
+RB_HD uint32_t tight_anchor_full(const TightCfg& c, TightState& t, const PlaneWord* cw, int w, int L, uint32_t xn) {
+    return anchor_word(cw, w, L, c.s, t.xc, xn, t.lenL);
 }
 
 // ---- phase B: window tests, component events, keep filter ---------------------------------------------------------------
@@ -147,7 +172,7 @@ struct TightOut {
     uint32_t x, s, el;  // surviving E bits, S mask of the word, E bits the prefilter elided
     int last;           // position of the latest S bit in front of the word
 };
-template <bool SMALL>
+template <int TIER>
 RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t passA, TightOut& o) {
     uint32_t sA, eA, sAp;
     ev_step(passA, t.ea, sA, eA, sAp);
@@ -158,7 +183,7 @@ RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t pas
         t.sm[i] = v;                                     \
         v = nv;                                          \
     }
-    if (SMALL) { RB_TSMEAR(0, c.d0) RB_TSMEAR(1, c.d1) RB_TSMEAR(2, c.d2) RB_TSMEAR(3, c.d3) }
+    if (TIER == TIER_SMALL) { RB_TSMEAR(0, c.d0) RB_TSMEAR(1, c.d1) RB_TSMEAR(2, c.d2) RB_TSMEAR(3, c.d3) }
     else { RB_TSMEAR(0, 1) RB_TSMEAR(1, 2) RB_TSMEAR(2, 4) RB_TSMEAR(3, 8) }
 #undef RB_TSMEAR
     o.x = eA & ~v; o.el = eA & v; o.s = sA; o.last = t.ea.lastS;

@@ -69,7 +69,7 @@ void pack(const char* seq, int64_t L, int guard, std::vector<PlaneWord>& pw) {
 
 // The kernel's tight_run for one item: the lanes step through scan_tight.h in lockstep, the warp-level operations
 // (votes, shuffles, ballots, reductions) are done across the lane arrays.
-template <bool SMALL>
+template <int TIER>
 long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const PlaneWord* cw, int& w, int wend, int L, ItemOut& io,
                std::vector<Meta>& meta) {
     const int bw = lay.bw;
@@ -77,7 +77,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
     TightCfg tc[32];
     for (int j = 0; j < bw; ++j) { tight_enter(cfg[j], st[j], ts[j]); tc[j] = make_tight_cfg(cfg[j]); }
     uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
-    bool susp = true, susc = true;
+    bool susp = true, susc = true, prev_rare = true;
     int zc = 0;
     long steps = 0;
     const int w_in = w;
@@ -89,11 +89,17 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
             const PlaneWord o = cw[w + 1], b = cw[w + 1 + (tc[j].s >> 5) + 1];
             bool sus;
             lenL0[j] = ts[j].lenL;
-            a[j] = tight_phaseA<SMALL>(tc[j], ts[j], o.h, o.l, b.h, b.l, xn[j], l1[j], sus);
+            a[j] = tight_phaseA<TIER>(tc[j], ts[j], o.h, o.l, b.h, b.l, xn[j], l1[j], sus);
             rare |= sus;
         }
-        if (!SMALL) { const bool r3 = rare | susc | susp; susp = susc; susc = rare; rare = r3; }
-        if (rare) for (int j = 0; j < bw; ++j) a[j] = tight_anchor_exact<SMALL>(tc[j], ts[j], cw, w, L, xn[j], lenL0[j]);
+        if (TIER != TIER_SMALL) { const bool r3 = rare | susc | susp; susp = susc; susc = rare; rare = r3; }
+        if (rare)
+            for (int j = 0; j < bw; ++j) {
+                bool full;
+                a[j] = tight_anchor_rare<TIER>(tc[j], ts[j], cw, w, L, xn[j], a[j], lenL0[j], prev_rare, full);
+                if (full) a[j] = tight_anchor_full(tc[j], ts[j], cw, w, L, xn[j]);
+            }
+        prev_rare = rare;
         for (int j = 0; j < bw; ++j) pair[j] = a[j] | a[j + 1 < bw ? j + 1 : j];
         uint32_t passS[32], passA[32], cand[32];
         TightOut oa[32], os[32];
@@ -101,7 +107,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
         for (int j = 0; j < bw; ++j) {
             const uint32_t an = pair[j >= 2 ? j - 2 : j] | pair[j + 1 < bw ? j + 1 : j];
             tight_windows(tc[j], ts[j], an, l1[j], passS[j], passA[j], cand[j]);
-            tight_events_A<SMALL>(tc[j], ts[j], 32 * w, passA[j], oa[j]);
+            tight_events_A<TIER>(tc[j], ts[j], 32 * w, passA[j], oa[j]);
             actS |= passS[j] != 0u;
         }
         for (int j = 0; j < bw; ++j) {
@@ -113,8 +119,8 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
         const uint32_t off = (uint32_t)io.raw.size();
         uint32_t elA = 0u, elS = 0u;
         for (int j = 0; j < bw; ++j) if (oa[j].x) io.raw.push_back(make_entry(STREAM_A, tc[j].s, oa[j].x, oa[j].s, oa[j].last));
-        for (int j = 0; j < bw; ++j) if (os[j].x) io.raw.push_back(make_entry(STREAM_S, tc[j].s, os[j].x, os[j].s, os[j].last));
         for (int j = 0; j < bw; ++j) if (cand[j]) io.raw.push_back(make_entry(STREAM_P, tc[j].s, cand[j], ts[j].xc & ~l1[j], 0));
+        for (int j = 0; j < bw; ++j) if (os[j].x) io.raw.push_back(make_entry(STREAM_S, tc[j].s, os[j].x, os[j].s, os[j].last));
         for (int j = 0; j < bw; ++j) { elA |= oa[j].el; elS |= os[j].el; }
         meta[w] = make_meta((int)(io.raw.size() - off), elS ? 32 - clz32(elS) : 0, elA ? 32 - clz32(elA) : 0, 0, off);
         for (int j = 0; j < bw; ++j) tight_rotate(ts[j], xn[j]);
@@ -122,7 +128,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
         ++w; ++steps;
     }
     for (int j = 0; j < bw; ++j) {
-        if (!SMALL && tc[j].s) ts[j].lenL = tight_lenL_lookup(tc[j], ts[j], cw, w);
+        if (TIER != TIER_SMALL && tc[j].s && !prev_rare) ts[j].lenL = tight_lenL_lookup(tc[j], ts[j], cw, w);
         tight_leave(ts[j], st[j]);
         if (w != w_in && cfg[j].s) st[j].xc.idx = w + (cfg[j].s >> 5) + 1;
     }
@@ -238,8 +244,10 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                     if (tight && w > we && w >= e0 && fastrun >= 4 && !prev_slow) {
                         const int wend = std::min(std::min(ch.w1, nw - 1), (((int)L - lay.s_hi) >> 5) - 1);
                         if (w < wend && (cw[w - 1].v & cw[w].v) == 0xFFFFFFFFu) {
-                            const bool small = band_m0(lay, band) - 2 <= 15;
-                            tight_steps += small ? run_tight<true>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band]) : run_tight<false>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band]);
+                            const int tier = tight_tier(band_m0(lay, band) - 2);
+                            tight_steps += tier == TIER_SMALL ? run_tight<TIER_SMALL>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band])
+                                         : tier == TIER_MID ? run_tight<TIER_MID>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band])
+                                                            : run_tight<TIER_LARGE>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band]);
                         }
                     }
                 }
