@@ -49,7 +49,7 @@ struct rb_ctx {
     const void* ascii_dev_ext = nullptr;
 
     DevBuf d_ascii, d_contigs, d_plane_start, d_bucket_base, d_planes, d_nmask, d_chunks, d_item_base, d_item_cap, d_item_count,
-        d_meta, d_bsum, d_item_clk, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys, d_text, d_ftiles, d_finfo, d_ftot, d_hpos, d_hseq;
+        d_meta, d_bcnt, d_item_clk, d_raw, d_counters, d_partial, d_dst, d_contig_off, d_totals, d_seeds, d_seedinfo, d_dst8, d_long, d_mitems, d_mkeys, d_text, d_ftiles, d_finfo, d_ftot, d_hpos, d_hseq;
     DevBatch batch{};
 
     // pinned host results
@@ -130,10 +130,10 @@ void make_chunks(rb_ctx* c, long long total_words, int range_first, int range_la
     const BandLayout& lay = c->lay;
     int cw = c->params.chunk_words;
     if (cw <= 0) {
-        // one-warp items (chunk x band), 16 resident per SM: about 32 waves of them keep the tail short; chunks of at least
-        // 256 words amortise the warm-up in front of every chunk, longer ones are not needed for that
-        const long long target_items = 148ll * 16 * 32;
-        cw = (int)std::min<long long>(8192, std::max<long long>(256, total_words * lay.nbands / target_items));
+        // one-warp items (chunk x band), 16 resident per SM: about 16 waves of them keep the tail short; chunks of at least
+        // 384 words amortise the warm-up in front of every chunk (about 25 word steps), longer ones are not needed for that
+        const long long target_items = 148ll * 16 * 16;
+        cw = (int)std::min<long long>(8192, std::max<long long>(384, total_words * lay.nbands / target_items));
     }
     c->chunks.clear();
     const int n = (int)c->contigs.size();
@@ -237,7 +237,7 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.n_merge_blocks = (int)((b.n_buckets + MERGE_BLOCK - 1) / MERGE_BLOCK);
     if ((rc = ensure(c, c->d_planes, (size_t)b.n_plane_words * sizeof(PlaneWord)))) return rc;
     if ((rc = ensure(c, c->d_meta, (size_t)b.n_buckets * c->lay.nbands * sizeof(Meta)))) return rc;
-    if ((rc = ensure(c, c->d_bsum, (size_t)std::max<long long>(b.n_buckets, 1) * sizeof(BucketSum)))) return rc;
+    if ((rc = ensure(c, c->d_bcnt, (size_t)std::max<long long>(b.n_buckets, 1) * c->lay.nbands * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(c, c->d_counters, 4 * sizeof(int)))) return rc;
     if ((rc = ensure(c, c->d_partial, ((size_t)b.n_merge_blocks + 1) * sizeof(BlockPartial)))) return rc;
     if ((rc = ensure(c, c->d_contig_off, 3 * ((size_t)n + 1) * sizeof(long long)))) return rc;
@@ -251,7 +251,7 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     b.nmask = (uint32_t*)c->d_nmask.p;
     b.chunks = (const Chunk*)c->d_chunks.p;
     b.meta = (Meta*)c->d_meta.p;
-    b.bsum = (BucketSum*)c->d_bsum.p;
+    b.bcnt = (uint32_t*)c->d_bcnt.p;
     b.counters = (int*)c->d_counters.p;
     b.partial = (BlockPartial*)c->d_partial.p;
     b.contig_off = (long long*)c->d_contig_off.p;
@@ -303,7 +303,7 @@ void rb_destroy(rb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_ascii, &c->d_contigs, &c->d_plane_start, &c->d_bucket_base, &c->d_planes, &c->d_nmask, &c->d_chunks,
-                      &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_bsum, &c->d_item_clk, &c->d_raw, &c->d_counters,
+                      &c->d_item_base, &c->d_item_cap, &c->d_item_count, &c->d_meta, &c->d_bcnt, &c->d_item_clk, &c->d_raw, &c->d_counters,
                       &c->d_partial, &c->d_dst, &c->d_contig_off, &c->d_totals, &c->d_seeds, &c->d_seedinfo, &c->d_dst8, &c->d_long, &c->d_mitems, &c->d_mkeys,
                       &c->d_text, &c->d_ftiles, &c->d_finfo, &c->d_ftot, &c->d_hpos, &c->d_hseq};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);

@@ -102,7 +102,8 @@ struct GpuSink {
     Rec* base;
     int cap;
     int* cnt;
-    int nslots;  // slots this lane wrote into this bucket
+    int nslots;        // slots this lane wrote into this bucket
+    int n[3];          // candidates per stream this lane put into this bucket
     int dS, dA;
     __device__ __forceinline__ void put(const Rec& r) {
         const int idx = atomicAdd(cnt, 1);
@@ -113,14 +114,17 @@ struct GpuSink {
         Rec r;
         r.start = start; r.end = end; r.mflags = mlen | (flags << 16) | (stream << REC_STREAM_SHIFT); r.key = key;
         put(r);
+        ++n[stream];
     }
     __device__ __forceinline__ void entry(int stream, int mlen, uint32_t mask, uint32_t smask, int last) {
         put(make_entry(stream, mlen, mask, smask, last));
+        n[stream] += __popc(mask);
     }
     __device__ __forceinline__ void dropped_mask(int stream, uint32_t el) {
         const int d = 32 - __clz((int)el);  // 0 when nothing was elided
         if (stream == STREAM_S) dS = max(dS, d); else dA = max(dA, d);
     }
+    __device__ __forceinline__ void reset() { nslots = 0; n[0] = n[1] = n[2] = 0; dS = 0; dA = 0; }
 };
 
 static const int SCAN_WARPS = 1;
@@ -147,6 +151,7 @@ struct TightIO {
     TightCfg c;
     const PlaneWord* cw;
     Meta* meta;        // bucket metadata of the item's (band, contig)
+    uint32_t* bcnt;    // candidate counts of the item's (band, contig)
     Rec* raw;          // raw pool
     uint32_t off;      // raw-pool index of the next slot of the item
     uint32_t cap_end;  // first index past the item's reservation
@@ -167,6 +172,18 @@ __device__ __noinline__ uint32_t tight_rare(const TightCfg& c, TightState& t, co
     return a;
 }
 
+// exact check of the survivors of the bit-parallel prefilters (scan_core.h kept_exact), out of line like the rare anchors
+struct ExactIO {
+    uint32_t xA, sA, xS, sS, cand, xc, sx;
+    int lastA, lastS;
+};
+__device__ __noinline__ void tight_exact(ExactIO* e, const PlaneWord* cw, int w, int s, uint32_t needA, uint32_t needS) {
+    const int p0 = 32 * w;
+    if (needA) e->xA = kept_exact(cut_anch(s), p0, e->xA, e->sA, e->lastA);
+    if (needS) e->xS = kept_exact(cut_subst(s), p0, e->xS, e->sS, e->lastS);
+    if (e->cand) e->cand = kept_exact_perfect(cw, w, s, cut_perfect(s), e->xc, e->sx, e->cand);
+}
+
 // everything the loop carries besides the per-word lane state
 struct TightLoop {
     TightCfg c;
@@ -175,6 +192,7 @@ struct TightLoop {
     const uint4* po;   // plane word w + 1 (all lanes)
     const uint2* pb;   // h / l of plane word w + 1 + (s >> 5) + 1 (per lane)
     Meta* mp;          // bucket metadata of word w
+    uint32_t* cp;      // candidate counts of word w
     uint32_t off, cap_end;
     int w, wend, L;
     uint32_t vprev, vcur;
@@ -236,19 +254,38 @@ __device__ __forceinline__ void tight_step(TightLoop& q, const TightState& in, T
     const uint32_t pair = a | __shfl_down_sync(FULL, a, 1);
     const uint32_t an = __shfl_up_sync(FULL, pair, 2) | __shfl_down_sync(FULL, pair, 1);
     uint32_t passS, passA, cand;
-    tight_windows(c, t, an, l1, passS, passA, cand);
+    tight_windows<TIER>(c, t, an, l1, passS, passA, cand);
     const int p0 = 32 * q.w;
     TightOut oa, os;
     tight_events_A<TIER>(c, t, p0, passA, oa);
-    const uint32_t elA = __reduce_or_sync(gmask, oa.el);
     cand &= c.mmask;
-    // mask entries: one slot per (lane, stream) with surviving candidates, packed by ballot
+    os.x = 0u; os.s = 0u; os.e = 0u; os.last = 0;
+    const bool on = WHOLE ? true : q.on;
+    // perfect and substitution candidates are rare: one vote decides whether their event logic runs at all
+    const bool anyPS = __any_sync(FULL, (cand | passS) != 0u);
+    const bool runS = anyPS || q.zc < 2;
+    if (runS) {
+        const bool actS = __any_sync(FULL, passS != 0u);
+        tight_events_S(t, p0, passS, os);
+        q.zc = actS ? 0 : q.zc + 1;
+    }
+    // survivors of the prefilters that are not decided yet: exact check, bit by bit (rare)
+    // (substitution stream: the prefilter is the cutoff itself while that is 10, i.e. for motif sizes up to 30)
+    const uint32_t needA = c.exactA ? 0u : oa.x, needS = c.s > 30 ? os.x : 0u;
+    if (__any_sync(FULL, (needA | needS | cand) != 0u)) {
+        ExactIO ex;
+        ex.xA = oa.x; ex.sA = oa.s; ex.lastA = oa.last; ex.xS = os.x; ex.sS = os.s; ex.lastS = os.last;
+        ex.cand = cand; ex.xc = t.xc; ex.sx = t.xc & ~l1;
+        tight_exact(&ex, q.cw, q.w, c.s, needA, needS);
+        oa.x = ex.xA; os.x = ex.xS; cand = ex.cand;
+    }
+    const uint32_t elA = __reduce_or_sync(gmask, oa.e & ~oa.x);
+    uint32_t counts = pack_counts(STREAM_A, __popc(oa.x));
+    // mask entries: one slot per (lane, stream) with candidates, packed by ballot
     const uint32_t off_in = q.off;
     uint32_t off = q.off;
-    const bool on = WHOLE ? true : q.on;
     const bool hA = on && oa.x != 0u;
     const unsigned balA = __ballot_sync(FULL, hA);
-    const bool anyPS = __any_sync(FULL, (cand | passS) != 0u);
     if (balA) {
         const unsigned mine = balA & gmask;
         const uint32_t pos = off + __popc(mine & lt);
@@ -256,33 +293,29 @@ __device__ __forceinline__ void tight_step(TightLoop& q, const TightState& in, T
         off += __popc(mine);
     }
     uint32_t elS = 0u;
-    // perfect and substitution candidates are rare: one vote covers both
-    if (anyPS || q.zc < 2) {
-        const bool hP = on && cand != 0u;
-        const unsigned balP = __ballot_sync(FULL, hP);
-        const bool actS = __any_sync(FULL, passS != 0u);
-        if (balP) {
-            const unsigned mine = balP & gmask;
-            const uint32_t pos = off + __popc(mine & lt);
-            if (hP && pos < q.cap_end) *reinterpret_cast<int4*>(q.raw + pos) = make_int4((int)cand, (int)(t.xc & ~l1), c.s | (REC_ENTRY << 16) | (STREAM_P << REC_STREAM_SHIFT), 0);
-            off += __popc(mine);
+    if (runS) {
+        const bool hP = on && cand != 0u, hS = on && os.x != 0u;
+        const unsigned balP = __ballot_sync(FULL, hP), balS = __ballot_sync(FULL, hS);
+        if (balP | balS) {
+            const unsigned mineP = balP & gmask, mineS = balS & gmask;
+            const uint32_t posP = off + __popc(mineP & lt);
+            if (hP && posP < q.cap_end) *reinterpret_cast<int4*>(q.raw + posP) = make_int4((int)cand, (int)(t.xc & ~l1), c.s | (REC_ENTRY << 16) | (STREAM_P << REC_STREAM_SHIFT), 0);
+            off += __popc(mineP);
+            const uint32_t posS = off + __popc(mineS & lt);
+            if (hS && posS < q.cap_end) *reinterpret_cast<int4*>(q.raw + posS) = make_int4((int)os.x, (int)os.s, c.s | (REC_ENTRY << 16) | (STREAM_S << REC_STREAM_SHIFT), os.last);
+            off += __popc(mineS);
+            counts += pack_counts(STREAM_P, __popc(cand)) + pack_counts(STREAM_S, __popc(os.x));
         }
-        tight_events_S(t, p0, passS, os);
-        q.zc = actS ? 0 : q.zc + 1;
-        const bool hS = on && os.x != 0u;
-        const unsigned balS = __ballot_sync(FULL, hS);
-        elS = __reduce_or_sync(gmask, os.el);
-        if (balS) {
-            const unsigned mine = balS & gmask;
-            const uint32_t pos = off + __popc(mine & lt);
-            if (hS && pos < q.cap_end) *reinterpret_cast<int4*>(q.raw + pos) = make_int4((int)os.x, (int)os.s, c.s | (REC_ENTRY << 16) | (STREAM_S << REC_STREAM_SHIFT), os.last);
-            off += __popc(mine);
-        }
+        elS = __reduce_or_sync(gmask, os.e & ~os.x);
     }
-    // every lane of the item stores the same word to the same address
-    if (on) *q.mp = make_meta((int)(off - off_in), 32 - __clz((int)elS), 32 - __clz((int)elA), 0, off_in);
+    counts = __reduce_add_sync(gmask, counts);
+    // every lane of the item stores the same words to the same addresses
+    if (on) {
+        *q.mp = make_meta((int)(off - off_in), 32 - __clz((int)elS), 32 - __clz((int)elA), 0, off_in);
+        *q.cp = counts;
+    }
     q.off = off;
-    ++q.mp;
+    ++q.mp; ++q.cp;
     tight_rotate(t, xn);
     q.vprev = q.vcur; q.vcur = o.w;
     ++q.w;
@@ -299,6 +332,7 @@ __device__ __noinline__ void tight_run(TightIO* io) {
     q.po = reinterpret_cast<const uint4*>(q.cw + (q.w + 1));
     q.pb = reinterpret_cast<const uint2*>(q.cw + (q.w + 1 + (q.c.s >> 5) + 1));
     q.mp = io->meta + q.w;
+    q.cp = io->bcnt + q.w;
     q.vprev = q.on ? q.cw[q.w - 1].v : 0xFFFFFFFFu; q.vcur = q.on ? q.cw[q.w].v : 0xFFFFFFFFu;
     // flags of the two words in front: unknown, so the first steps take the exact anchors; t.lenL is the general path's
     // carried run length
@@ -350,6 +384,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     LaneCfg cfg = band_lane_cfg(b.lay, band, j);
     lane_cfg_set_contig(cfg, L);
     Meta* __restrict__ meta = b.meta + (long long)band * b.n_buckets + b.bucket_base[ch.contig];
+    uint32_t* __restrict__ bcnt = b.bcnt + (long long)band * b.n_buckets + b.bucket_base[ch.contig];
     int* cnt = &s_cnt[warp][g];
 
     GpuSink sk;
@@ -369,7 +404,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             if (bits != gmask) alln = false;
         }
         if (alln) {
-            for (int wq = ch.w0 + j; wq < ch.w1; wq += BW) meta[wq] = make_meta(0, 0, 0, 1, off0);
+            for (int wq = ch.w0 + j; wq < ch.w1; wq += BW) { meta[wq] = make_meta(0, 0, 0, 1, off0); bcnt[wq] = 0u; }
             if (j == 0) b.item_count[item] = 0;
             active = false;
         }
@@ -425,7 +460,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     if (active && ch.w0 >= ch.w1) {  // empty contig: only the tail bucket
         active = false;
         if (ch.last) {
-            if (j == 0) meta[ch.w1] = make_meta(0, 0, 0, 1, off0);
+            if (j == 0) { meta[ch.w1] = make_meta(0, 0, 0, 1, off0); bcnt[ch.w1] = 0u; }
         }
         if (j == 0) b.item_count[item] = 0;
     }
@@ -439,11 +474,15 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
         // ---- end of the chunk: tail flush (last chunk of a contig), slot count ---------------------------------
         if (active && w >= ch.w1) {
             if (ch.last) {
-                sk.nslots = 0;
+                sk.reset();
                 lane_tail(sk, cfg, st, L);
                 const int ns = __reduce_add_sync(gmask, sk.nslots);
-                if (j == 0) meta[ch.w1] = make_meta(min(ns, META_MAX_SLOTS), 0, 0, 1, off);
-                if (ns > META_MAX_SLOTS && j == 0) atomicAdd(b.counters + 2, 1);
+                const int nP = __reduce_add_sync(gmask, sk.n[0]), nS = __reduce_add_sync(gmask, sk.n[1]), nA = __reduce_add_sync(gmask, sk.n[2]);
+                if (j == 0) {
+                    meta[ch.w1] = make_meta(min(ns, META_MAX_SLOTS), 0, 0, 1, off);
+                    bcnt[ch.w1] = pack_counts(STREAM_P, nP) + pack_counts(STREAM_S, nS) + pack_counts(STREAM_A, nA);
+                    if (ns > META_MAX_SLOTS || counts_overflow(nP, nS, nA)) atomicAdd(b.counters + 2, 1);
+                }
             }
             __syncwarp(gmask);
             if (j == 0) {
@@ -537,13 +576,17 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
         } else if (active) {
             IterCtx it;
             it.w = w; it.L = L; it.emit_on = w >= we && w >= e0; it.slow = slow; it.prev_slow = prev_slow; it.fastrun = fastrun;
-            sk.nslots = 0; sk.dS = 0; sk.dA = 0;
+            sk.reset();
             lane_phase2(sk, cfg, st, cw, it, a_m2, a_m1, a_p1, a_p2, w >= q + Ha);
             if (it.emit_on) {
                 const int ns = __reduce_add_sync(gmask, sk.nslots);
+                const int nP = __reduce_add_sync(gmask, sk.n[0]), nS = __reduce_add_sync(gmask, sk.n[1]), nA = __reduce_add_sync(gmask, sk.n[2]);
                 const int dS = __reduce_max_sync(gmask, sk.dS), dA = __reduce_max_sync(gmask, sk.dA);
-                if (j == 0) meta[w] = make_meta(min(ns, META_MAX_SLOTS), dS, dA, it.slow, off);
-                if (ns > META_MAX_SLOTS && j == 0) atomicAdd(b.counters + 2, 1);
+                if (j == 0) {
+                    meta[w] = make_meta(min(ns, META_MAX_SLOTS), dS, dA, it.slow, off);
+                    bcnt[w] = pack_counts(STREAM_P, nP) + pack_counts(STREAM_S, nS) + pack_counts(STREAM_A, nA);
+                    if (ns > META_MAX_SLOTS || counts_overflow(nP, nS, nA)) atomicAdd(b.counters + 2, 1);
+                }
                 off += (uint32_t)ns;
             }
             prev_slow = slow;
@@ -562,7 +605,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             TightIO io;
             tight_enter(cfg, st, io.t);
             io.c = make_tight_cfg(cfg);
-            io.cw = cw; io.meta = meta; io.raw = b.raw; io.off = off; io.cap_end = off0 + (uint32_t)sk.cap;
+            io.cw = cw; io.meta = meta; io.bcnt = bcnt; io.raw = b.raw; io.off = off; io.cap_end = off0 + (uint32_t)sk.cap;
             io.w = w; io.wend = wend; io.L = L; io.on = want ? 1 : 0;
             io.lt = (1u << lane) - 1u;
             if (tier == TIER_SMALL) tight_run<BW, TIER_SMALL>(&io);
@@ -603,10 +646,20 @@ struct BucketInfo {
     unsigned long long emax[2];     // contig << 32 | elided_end_code
 };
 
-__device__ __forceinline__ BucketInfo bucket_info_from(const DevBatch& b, long long gb, const unsigned (&tot)[3], int slow, int dS, int dA) {
+__device__ __forceinline__ BucketInfo bucket_info(const DevBatch& b, long long gb) {
     BucketInfo bi;
     bi.c = find_segment(b.bucket_base, b.n_contigs, gb);
     bi.w = (int)(gb - b.bucket_base[bi.c]);
+    unsigned tot[3] = {0u, 0u, 0u};
+    int slow = 0, dS = 0, dA = 0;
+    for (int k = 0; k < b.lay.nbands; ++k) {
+        const Meta m = b.meta[(long long)k * b.n_buckets + gb];
+        const uint32_t cn = b.bcnt[(long long)k * b.n_buckets + gb];
+        tot[0] += counts_of(cn, 0); tot[1] += counts_of(cn, 1); tot[2] += counts_of(cn, 2);
+        slow |= meta_slow(m);
+        dS = max(dS, meta_dmax(m, STREAM_S));
+        dA = max(dA, meta_dmax(m, STREAM_A));
+    }
     for (int s = 0; s < 3; ++s) {
         bi.pseudo[s] = bucket_has_pseudo(s, slow, (int)tot[s]) ? 1u : 0u;
         bi.n[s] = tot[s] + bi.pseudo[s];
@@ -615,12 +668,6 @@ __device__ __forceinline__ BucketInfo bucket_info_from(const DevBatch& b, long l
     bi.emax[0] = eS ? (((unsigned long long)bi.c << 32) | eS) : 0ull;
     bi.emax[1] = eA ? (((unsigned long long)bi.c << 32) | eA) : 0ull;
     return bi;
-}
-// from the per-bucket summary merge_count_kernel left behind
-__device__ __forceinline__ BucketInfo bucket_info(const DevBatch& b, long long gb) {
-    const BucketSum bs = b.bsum[gb];
-    const unsigned tot[3] = {bs.n[0], bs.n[1], bs.n[2]};
-    return bucket_info_from(b, gb, tot, bs.dS >> 7, bs.dS & 0x3F, bs.dA & 0x3F);
 }
 
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
@@ -661,49 +708,12 @@ __device__ __forceinline__ void block_scan(const unsigned (&n)[3], const unsigne
     }
 }
 
-// thread = bucket: expands the mask entries of the bucket far enough to know which candidates reach the consumer's cutoff
-// (the kept mask replaces the entry's E mask in the raw pool), counts the bucket's records per stream, leaves the bucket
-// summary for merge_write_kernel and the block sums for the prefix.
 __global__ void __launch_bounds__(MERGE_BLOCK) merge_count_kernel(DevBatch b) {
     const long long gb = b.gb_first + (long long)blockIdx.x * MERGE_BLOCK + threadIdx.x;
     unsigned n[3] = {0u, 0u, 0u};
     unsigned long long e[2] = {0ull, 0ull};
     if (gb < b.gb_first + b.n_active) {
-        const int c = find_segment(b.bucket_base, b.n_contigs, gb);
-        const int w = (int)(gb - b.bucket_base[c]);
-        const PlaneWord* __restrict__ cw = b.planes + b.contigs[c].word_base;
-        unsigned tot[3] = {0u, 0u, 0u};
-        int slow = 0, dS = 0, dA = 0;
-        for (int k = 0; k < b.lay.nbands; ++k) {
-            const Meta m = b.meta[(long long)k * b.n_buckets + gb];
-            const int ns = meta_slots(m);
-            slow |= meta_slow(m);
-            dS = max(dS, meta_dmax(m, STREAM_S));
-            dA = max(dA, meta_dmax(m, STREAM_A));
-            for (int i = 0; i < ns; ++i) {
-                Rec* rp = b.raw + m.off + i;
-                const int4 v = *reinterpret_cast<const int4*>(rp);
-                Rec r;
-                r.start = v.x; r.end = v.y; r.mflags = v.z; r.key = v.w;
-                const int st = rec_stream(r);
-                if (rec_is_entry(r)) {
-                    int el;
-                    const uint32_t kept = entry_kept_mask(r, w, cw, el);
-                    if (kept != (uint32_t)r.start) rp->start = (int)kept;
-                    tot[st] += (unsigned)__popc(kept);
-                    if (st == STREAM_S) dS = max(dS, el);
-                    if (st == STREAM_A) dA = max(dA, el);
-                } else {
-                    tot[st] += 1u;
-                }
-            }
-        }
-        BucketSum bs;
-        for (int s = 0; s < 3; ++s) bs.n[s] = (unsigned short)min(tot[s], 0xFFFFu);
-        if (tot[0] > 0xFFFFu || tot[1] > 0xFFFFu || tot[2] > 0xFFFFu) atomicAdd(b.counters + 2, 1);
-        bs.dS = (unsigned char)(dS | (slow << 7)); bs.dA = (unsigned char)dA;
-        b.bsum[gb] = bs;
-        const BucketInfo bi = bucket_info_from(b, gb, tot, slow, dS, dA);
+        const BucketInfo bi = bucket_info(b, gb);
         for (int s = 0; s < 3; ++s) n[s] = bi.n[s];
         e[0] = bi.emax[0]; e[1] = bi.emax[1];
     }
@@ -771,7 +781,7 @@ __global__ void __launch_bounds__(1024) merge_scan_kernel(DevBatch b) {
 
 // Phase 1 (thread = bucket): stream offsets of every bucket of the block, pseudo records, per-contig offsets.
 // Phase 2 (thread = slot): the block's raw slots are spread evenly over the threads; each finds its bucket in the shared
-// prefix table; every candidate of the slot (one for a record, the kept bits of a mask entry) ranks itself among the
+// prefix table; every candidate of the slot (one for a record, the set bits of a mask entry) ranks itself among the
 // bucket's candidates of its stream by (time, mlen, seq) and is written in its final form.
 __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     __shared__ uint32_t s_off[8][MERGE_BLOCK];          // first raw slot of (band, bucket)
@@ -854,40 +864,39 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
         int band = 0;
         while (idx >= s_n[band][bk]) { idx -= s_n[band][bk]; ++band; }
         const int4 v = *reinterpret_cast<const int4*>(b.raw + s_off[band][bk] + idx);
-        Rec rec;
-        rec.start = v.x; rec.end = v.y; rec.mflags = v.z; rec.key = v.w;
-        const int st = rec_stream(rec);
-        const bool is_entry = rec_is_entry(rec);
-        const int w = s_w[bk], mlen = rec_mlen(rec);
+        const int st = (v.z >> REC_STREAM_SHIFT) & 3;
+        const bool is_entry = ((v.z >> 16) & REC_ENTRY) != 0;
+        const int w = s_w[bk], mlen = v.z & 0xFFFF;
         const long long dbase = sbase[st] + (long long)bp.sum[st] + s_dst[st][bk];
-        uint32_t bits = is_entry ? (uint32_t)rec.start : 1u;
-        const PlaneWord* cw = nullptr;
-        if (is_entry && bits) cw = b.planes + b.contigs[s_c[bk]].word_base;
-        while (bits) {
+        const uint32_t mk = (uint32_t)mlen << 2;
+        for (uint32_t bits = is_entry ? (uint32_t)v.x : 1u; bits; bits &= bits - 1u) {
             const int i = __ffs((int)bits) - 1;
-            bits &= bits - 1u;
-            const uint32_t key = is_entry ? entry_key(i, mlen) : (uint32_t)rec.key;
+            const uint32_t key = is_entry ? (((uint32_t)i << 18) | mk) : (uint32_t)v.w;
+            const int ki = (int)(key >> 18);
+            const uint32_t lowkey = key & 0x3FFFFu;
             int rank = 0;
             for (int k = 0; k < nbands; ++k) {
                 const int n = s_n[k][bk];
                 const int4* q = reinterpret_cast<const int4*>(b.raw + s_off[k][bk]);
                 for (int u = 0; u < n; ++u) {
                     const int4 ov = q[u];
-                    Rec o;
-                    o.start = ov.x; o.end = ov.y; o.mflags = ov.z; o.key = ov.w;
-                    if (rec_stream(o) == st) rank += slot_count_below(o, key);
+                    if (((ov.z >> REC_STREAM_SHIFT) & 3) != st) continue;
+                    if ((ov.z >> 16) & REC_ENTRY) rank += __popc((uint32_t)ov.x & lowmask(ki + ((((uint32_t)(ov.z & 0xFFFF)) << 2) < lowkey ? 1 : 0)));
+                    else rank += (uint32_t)ov.w < key ? 1 : 0;
                 }
             }
-            Rec out;
+            int4 out;
             if (is_entry) {
-                entry_interval(rec, w, cw, i, out.start, out.end);
-                out.mflags = mlen;
-                out.key = 32 * w + i;
+                Rec e;
+                e.start = v.x; e.end = v.y; e.mflags = v.z; e.key = v.w;
+                int s0, e0;
+                entry_interval(e, w, b.planes + b.contigs[s_c[bk]].word_base, i, s0, e0);
+                out = make_int4(s0, e0, mlen, 32 * w + i);
             } else {
-                out = finalize_rec(rec, w);
+                out = make_int4(v.x, v.y, v.z & ((1 << REC_STREAM_SHIFT) - 1), 32 * w + (v.w >> 18));
             }
             const long long at = dbase + rank;
-            if (at < b.dst_cap) *reinterpret_cast<int4*>(b.dst + at) = make_int4(out.start, out.end, out.mflags, out.key);
+            if (at < b.dst_cap) *reinterpret_cast<int4*>(b.dst + at) = out;
         }
     }
 }

@@ -16,12 +16,6 @@ struct BlockPartial {
     unsigned long long emax[2];  // contig << 32 | elided_end_code, streams S and A
 };
 
-// per-bucket summary merge_count leaves for merge_write: records per stream (pseudo records excluded), elided maxima
-struct BucketSum {
-    unsigned short n[3];
-    unsigned char dS, dA;  // dmax of the bucket per window stream (merge_core.h); bit 7 of dS: slow bucket
-};
-
 struct DevBatch {
     BandLayout lay;
     int n_contigs;
@@ -45,7 +39,7 @@ struct DevBatch {
     const int* item_cap;            // [n_items]
     int* item_count;                // [n_items] records the item produced (may exceed item_cap: overflow)
     Meta* meta;                     // [nbands][n_buckets]
-    BucketSum* bsum;                // [n_buckets]
+    uint32_t* bcnt;                 // [nbands][n_buckets] candidates per stream of (band, bucket): merge_core.h pack_counts
     Rec* raw;                       // raw slot pool
     long long* item_clk;            // diagnostics (rb_debug_item_clocks): [n_items][2] start / end of the item in globaltimer ns, or null
     int* counters;                  // [0] overflowed items, [1] warm-up restarts, [2] a count field overflowed (error)

@@ -21,7 +21,8 @@ namespace rb {
 // off  = index of the bucket's first slot in the raw pool (slots of one bucket are contiguous, the three streams
 //        interleaved in arrival order; Rec::mflags bits 28-29 hold the stream)
 // info = nslots | dmaxS << 12 | dmaxA << 18 | slow << 24; dmax = 1 + (latest emission time - 32*w) over the fast-word
-//        candidates the scan's prefilters elided (below the consumer's length cutoff), 0 = none
+//        candidates that were elided (below the consumer's length cutoff), 0 = none
+// Beside it, per (band, bucket), the candidate counts per stream: nP | nS << 10 | nA << 20 (pack_counts).
 struct alignas(8) Meta {
     uint32_t off, info;
 };
@@ -36,6 +37,12 @@ RB_HD Meta make_meta(int nslots, int dS, int dA, int slow, uint32_t off) {
     m.info = (uint32_t)nslots | ((uint32_t)dS << 12) | ((uint32_t)dA << 18) | ((uint32_t)slow << 24);
     return m;
 }
+
+RB_HD uint32_t pack_counts(int stream, int n) { return (uint32_t)n << (10 * stream); }
+RB_HD int counts_of(uint32_t c, int stream) { return stream == STREAM_A ? (int)(c >> 20) : (int)((c >> (10 * stream)) & 0x3FFu); }
+// a field of the summed counts overflowed (more than 1023 perfect / substitution or 4095 anchored candidates in one
+// (band, word)): cannot happen in fast words (29 motif lanes x 32 positions = 928), checked for slow words
+RB_HD bool counts_overflow(int nP, int nS, int nA) { return nP > 0x3FF || nS > 0x3FF || nA > 0xFFF; }
 
 RB_HD int rec_stream(const Rec& r) { return (r.mflags >> REC_STREAM_SHIFT) & 3; }
 RB_HD int rec_mlen(const Rec& r) { return r.mflags & 0xFFFF; }

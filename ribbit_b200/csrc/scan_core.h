@@ -120,32 +120,36 @@ struct LaneCfg {
     int cutS;    // substitution keep cutoff  (m>30 ? m/3 : 10)                   parse_substitute_shiftxor.cpp:423
     int cutA;    // anchored keep cutoff                                          parse_anchored_shiftxor.cpp:572-573
     int wm;      // first word whose anchor view differs from X_s (positions >= L-s are forced to 1); per contig
-    uint32_t dA; // smear shifts of the anchored keep filter, 6 bits each (smear_shifts)
+    uint32_t dA; // smear shifts of the anchored keep filter, 6 bits each (smear_shifts): levels 0-4
+    uint32_t dA2; //   levels 5-6
 };
 
 // consumer cutoffs
 RB_HD int cut_perfect(int m) { return m <= 6 ? 12 - m : m; }        // parse_perfect_shiftxor.cpp:193,216
 RB_HD int cut_subst(int m) { return m > 30 ? m / 3 : 10; }          // parse_substitute_shiftxor.cpp:423
 RB_HD int cut_anch(int m) {                                         // parse_anchored_shiftxor.cpp:572-573
+    // the reference computes (int)(0.9 * m) in double; 9 m / 10 in integers is the same number for every m up to 2000
+    // (tests/test_oracle.py checks it), and keeps double arithmetic out of the kernels
     int c = m > 6 ? m : 10;
-    if (m >= 10) c = (int)(0.9 * m);
+    if (m >= 10) c = (9 * m) / 10;
     return c;
 }
-static const int SMEAR_MAX = 16;  // positions the anchored keep filter looks back (exact for cutoffs up to this)
+static const int SMEAR_MAX = 96;  // positions the anchored keep filter looks back (exact for cutoffs up to this)
 
-// Shifts d_0..d_3 that smear a bit over exactly n <= 16 positions by doubling: with c_0 = 1, d_i = min(c_i, n - c_i),
-// c_{i+1} = c_i + d_i. Packed 6 bits each.
-RB_HD uint32_t smear_shifts(int n) {
-    uint32_t lo = 0u;
+// Shifts d_0..d_6 (each <= 32) that smear a bit over exactly n <= 96 positions by doubling: with c_0 = 1,
+// d_i = min(c_i, n - c_i, 32), c_{i+1} = c_i + d_i. Packed 6 bits each: d_0..d_4 in lo, d_5..d_6 in hi. For n >= 16 the
+// first four are 1, 2, 4, 8.
+RB_HD void smear_shifts(int n, uint32_t& lo, uint32_t& hi) {
+    lo = 0u; hi = 0u;
     if (n < 1) n = 1;
     if (n > SMEAR_MAX) n = SMEAR_MAX;
     int c = 1;
-    for (int i = 0; i < 4; ++i) {
-        const int d = (n - c < c) ? n - c : c;
-        lo |= (uint32_t)d << (6 * i);
+    for (int i = 0; i < 7; ++i) {
+        int d = (n - c < c) ? n - c : c;
+        if (d > 32) d = 32;
+        if (i < 5) lo |= (uint32_t)d << (6 * i); else hi |= (uint32_t)d << (6 * (i - 5));
         c += d;
     }
-    return lo;
 }
 
 RB_HD LaneCfg make_lane_cfg(int s, int m_lo, int m_hi, int s_lo, int s_hi, int band_m0, int band_m1) {
@@ -157,7 +161,7 @@ RB_HD LaneCfg make_lane_cfg(int s, int m_lo, int m_hi, int s_lo, int s_hi, int b
     c.cutS = cut_subst(s);
     c.cutA = cut_anch(s);
     c.wm = 0;
-    c.dA = smear_shifts(c.cutA);
+    smear_shifts(c.cutA, c.dA, c.dA2);
     return c;
 }
 // per-contig part of the lane configuration
@@ -377,7 +381,7 @@ struct LaneState {
     int pst;                        // perfect machine: start of the open run or -1 (last_starts); slow words
     WinState S, A;                  // valid while the previous word was a slow word
     EvCarry es, ea;                 // carries always valid; lastS valid while the previous word was a fast word
-    uint32_t sm[4];                 // anchored keep filter: previous word of each smear level
+    uint32_t sm[7];                 // anchored keep filter: previous word of each smear level
     XCache xc;
     // warm-up bookkeeping (chunks that do not start at the contig start)
     int sync;                       // bit0 anchors exact, bit1 perfect, bit2 subst, bit3 anchored
@@ -420,20 +424,23 @@ RB_HD void emit_perfect(Sink& sk, const IterCtx& it, const LaneCfg& cfg, int sta
 
 // Anchored keep filter. M1[t] = OR of S[t-k], k = 1..n, n = min(cutA, SMEAR_MAX): an E bit with M1 set belongs to a
 // component whose S bit is at most n positions back, i.e. whose length t - ts - 1 is below the consumer's cutoff
-// (parse_anchored_shiftxor.cpp:153). Exact for cutA <= SMEAR_MAX, else a prefilter (survivors are checked when the
-// entry is expanded, merge_core.h). Valid when this and the previous word are fast words.
+// (parse_anchored_shiftxor.cpp:153). Exact for cutA <= SMEAR_MAX, else a prefilter. Valid when the last four words were
+// fast words (it looks back up to three words).
 RB_HD uint32_t smear_step(const LaneCfg& cfg, LaneState& st, uint32_t S, uint32_t Sprev) {
     uint32_t v = fsl(Sprev, S, 1);
-#define RB_SMEAR_LEVEL(i, d)                                 \
-    {                                                        \
-        const uint32_t nv = v | fsl(st.sm[i], v, (int)(d)); \
-        st.sm[i] = v;                                        \
-        v = nv;                                              \
+#define RB_SMEAR_LEVEL(i, d)                                  \
+    {                                                         \
+        const uint32_t nv = v | fslc(st.sm[i], v, (int)(d)); \
+        st.sm[i] = v;                                         \
+        v = nv;                                               \
     }
     RB_SMEAR_LEVEL(0, cfg.dA & 63u)
     RB_SMEAR_LEVEL(1, (cfg.dA >> 6) & 63u)
     RB_SMEAR_LEVEL(2, (cfg.dA >> 12) & 63u)
     RB_SMEAR_LEVEL(3, (cfg.dA >> 18) & 63u)
+    RB_SMEAR_LEVEL(4, (cfg.dA >> 24) & 63u)
+    RB_SMEAR_LEVEL(5, cfg.dA2 & 63u)
+    RB_SMEAR_LEVEL(6, (cfg.dA2 >> 6) & 63u)
 #undef RB_SMEAR_LEVEL
     return v;
 }
@@ -486,6 +493,35 @@ RB_HD int perfect_run_start(const PlaneWord* cw, int w, int i, int s, uint32_t x
         if (z) return 32 * k + 32 - clz32(z);
     }
     return 0;
+}
+
+// Exact keep filters of a fast word (the consumer's length cutoffs): the bits of x (E bits that survived the bit-parallel
+// prefilters; perfect stream: run ends that follow six ones) whose candidate reaches `cut`.
+// window streams: the component emitted at E-bit i is (ls, le) = (ts - 7, p0 + i - 8), ts = the latest S bit before i
+RB_HD uint32_t kept_exact(int cut, int p0, uint32_t x, uint32_t S, int lastS) {
+    uint32_t kept = 0u;
+    while (x) {
+        const int i = ctz32(x);
+        x &= x - 1u;
+        const uint32_t sb = S & lowmask(i);
+        const int ts = sb ? p0 + 31 - clz32(sb) : lastS;
+        if (p0 + i - ts - 1 >= cut) kept |= 1u << i;
+    }
+    return kept;
+}
+// perfect stream: the run that ends at p0 + i started at the latest run start before i (sx = run starts of the word,
+// xw = X_s[w]); parse_perfect_shiftxor.cpp:190-208
+RB_HD uint32_t kept_exact_perfect(const PlaneWord* cw, int w, int s, int cut, uint32_t xw, uint32_t sx, uint32_t cand) {
+    uint32_t kept = 0u;
+    const int p0 = 32 * w;
+    while (cand) {
+        const int i = ctz32(cand);
+        cand &= cand - 1u;
+        const uint32_t sb = sx & lowmask(i);
+        const int a = sb ? p0 + 31 - clz32(sb) : perfect_run_start(cw, w, i, s, xw);
+        if (p0 + i - a >= cut) kept |= 1u << i;
+    }
+    return kept;
 }
 
 // All three machines of a motif lane at a fast -> slow transition in front of word w (x_prev = X_m[w-1] already rotated).
@@ -674,8 +710,8 @@ RB_HD uint32_t lane_phase1_fast_seq(const LaneCfg& cfg, LaneState& st, const Pla
 // Phase 2 of a fast word (it.slow == 0, machines on): every window is evaluated, so o.v is all ones and the N plane is
 // not consulted.
 template <class Sink>
-RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const IterCtx& it, uint32_t a_m2, uint32_t a_m1,
-                            uint32_t a_p1, uint32_t a_p2) {
+RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, const IterCtx& it, uint32_t a_m2,
+                            uint32_t a_m1, uint32_t a_p1, uint32_t a_p2) {
     if (cfg.motif) {
         const uint32_t x = st.x_cur;
         const uint32_t l1 = fsl(st.x_prev, x, 1);
@@ -702,9 +738,14 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const I
         // prefilters: a substitution component whose S bit is 9 or 10 back has length 8 or 9, below every cutoff
         // (parse_substitute_shiftxor.cpp:423: >= 10); the smear looks back into the previous word: trust it once a few
         // fast words in a row were seen
-        const uint32_t xS = it.emit_on ? (eS & ~(fsl(sSp, sS, 9) | fsl(sSp, sS, 10))) : 0u;
-        const uint32_t xA = it.emit_on ? (eA & ~(it.fastrun >= 4 ? killA : 0u)) : 0u;
-        if (it.emit_on && cand) sk.entry(STREAM_P, cfg.s, cand, x & ~l1, 0);
+        uint32_t xS = it.emit_on ? (eS & ~(fsl(sSp, sS, 9) | fsl(sSp, sS, 10))) : 0u;
+        uint32_t xA = it.emit_on ? (eA & ~(it.fastrun >= 4 ? killA : 0u)) : 0u;
+        uint32_t xP = it.emit_on ? cand : 0u;
+        // the survivors are checked exactly, so that an entry only holds candidates the consumer keeps
+        if (xS) xS = kept_exact(cfg.cutS, p0, xS, sS, st.es.lastS);
+        if (xA && (cfg.cutA > SMEAR_MAX || it.fastrun < 4)) xA = kept_exact(cfg.cutA, p0, xA, sA, st.ea.lastS);
+        if (xP) xP = kept_exact_perfect(cw, it.w, cfg.s, cfg.cutP, x, x & ~l1, xP);
+        if (xP) sk.entry(STREAM_P, cfg.s, xP, x & ~l1, 0);
         if (xS) sk.entry(STREAM_S, cfg.s, xS, sS, st.es.lastS);
         if (xA) sk.entry(STREAM_A, cfg.s, xA, sA, st.ea.lastS);
         sk.dropped_mask(STREAM_S, eS & ~xS);
@@ -721,7 +762,7 @@ template <class Sink>
 RB_HD void lane_phase2(Sink& sk, const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, const IterCtx& it,
                        uint32_t a_m2, uint32_t a_m1, uint32_t a_p1, uint32_t a_p2, int machines_on) {
     if (!it.slow && machines_on) {
-        lane_phase2_fast(sk, cfg, st, it, a_m2, a_m1, a_p1, a_p2);
+        lane_phase2_fast(sk, cfg, st, cw, it, a_m2, a_m1, a_p1, a_p2);
         return;
     }
     if (cfg.motif) {
@@ -796,7 +837,7 @@ RB_HD void lane_init(const LaneCfg& cfg, LaneState& st, const PlaneWord* cw, int
     st.es.S = 0u;
     st.es.lastS = -1;
     st.ea = st.es;
-    for (int i = 0; i < 4; ++i) st.sm[i] = 0u;
+    for (int i = 0; i < 7; ++i) st.sm[i] = 0u;
     st.xc.h = st.xc.l = 0u; st.xc.idx = -0x40000000;
     st.sync = (q == 0) ? SYNC_ALL : 0;
     st.zS = st.zA = 0;

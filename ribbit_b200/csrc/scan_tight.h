@@ -3,8 +3,9 @@
 // lane_phase1_fast / lane_phase2_fast), written for a minimal instruction stream:
 //   * all carries of the bit-sliced window counters, of the component start / end detection and of the keep filter stay
 //     in registers in their funnel-shift-ready form (TightState); nothing is recomputed from the previous word;
-//   * no per-bit work and no per-lane loops: a lane's candidates leave as mask entries (merge_core.h), the consumer's
-//     cutoff is applied when the ordered compaction expands them;
+//   * no per-lane emission loops: a lane's candidates leave as mask entries (merge_core.h) that the ordered compaction
+//     expands; the consumer's cutoff is exact in the bit-parallel filter for small motif sizes, the few survivors of the
+//     other lanes are checked bit by bit in a rarely taken region;
 //   * anchors (parse_anchored_shiftxor.cpp:20-56) in straight-line code; the run-length bound "< 2s" is only evaluated
 //     when a lane of the item sees a run that could reach it (bands whose smallest shift is >= 17: a half word of ones;
 //     the band with the small shifts: exact edge logic), which is rare outside repeats;
@@ -20,9 +21,11 @@ namespace rb {
 struct TightCfg {
     int s, sh;           // shift, s & 31
     int K2;              // 2 s (anchor run-length bound)
+    int exactA;          // the bit-parallel anchored keep filter is exact for this lane (cutA <= SMEAR_MAX)
     uint32_t amask;      // ~0 for lanes that own a shift, 0 for idle lanes (their anchors must read as 0)
     uint32_t mmask;      // ~0 for motif lanes
-    int d0, d1, d2, d3;  // smear shifts of the anchored keep filter (SMALL items; else 1, 2, 4, 8)
+    int d0, d1, d2, d3;  // smear shifts of the anchored keep filter, levels 0-3 (SMALL items; else 1, 2, 4, 8)
+    int d4, d5, d6;      //   levels 4-6
     int e0, e1, e2, e3, e4;  // doubling shifts of "K2 ones in a row" (SMALL items)
 };
 
@@ -33,15 +36,18 @@ struct TightState {
     WinCarryS cs;
     WinCarryA ca;
     EvCarry es, ea;
-    uint32_t sm[4];
+    uint32_t sm[7];
+    uint32_t p8, p16;      // MID / LARGE: previous word of "8 / 16 ones of X_s in a row end here" (perfect-run prefilter)
 };
 
 RB_HD TightCfg make_tight_cfg(const LaneCfg& c) {
     TightCfg t;
     t.s = c.s; t.sh = c.s & 31; t.K2 = 2 * c.s;
+    t.exactA = c.cutA <= SMEAR_MAX;
     t.amask = c.s ? 0xFFFFFFFFu : 0u;
     t.mmask = c.motif ? 0xFFFFFFFFu : 0u;
     t.d0 = (int)(c.dA & 63u); t.d1 = (int)((c.dA >> 6) & 63u); t.d2 = (int)((c.dA >> 12) & 63u); t.d3 = (int)((c.dA >> 18) & 63u);
+    t.d4 = (int)((c.dA >> 24) & 63u); t.d5 = (int)(c.dA2 & 63u); t.d6 = (int)((c.dA2 >> 6) & 63u);
     // five doubling steps reach min(K2, 32) ones in a row
     int k = 1, e[5];
     for (int i = 0; i < 5; ++i) {
@@ -58,18 +64,22 @@ RB_HD TightCfg make_tight_cfg(const LaneCfg& c) {
 RB_HD void tight_enter(const LaneCfg& cfg, const LaneState& st, TightState& t) {
     t.xp = st.x_prev; t.xc = st.x_cur; t.bh = st.xc.h; t.bl = st.xc.l; t.lenL = st.lenL;
     t.cs = st.cs; t.ca = st.ca; t.es = st.es; t.ea = st.ea;
-    for (int i = 0; i < 4; ++i) t.sm[i] = st.sm[i];
+    for (int i = 0; i < 7; ++i) t.sm[i] = st.sm[i];
+    // 8 / 16 ones in a row ending at t, from the previous word alone: exact in the top bits, which is all that is read
+    uint32_t a = t.xp & (t.xp << 1);
+    a &= a << 2; a &= a << 4;
+    t.p8 = a; t.p16 = a & (a << 8);
     if (!cfg.motif) {
         // the general path keeps no event state for shifts that are not motif sizes: theirs reads "nothing ever passed"
         t.es.P = 0u; t.es.S = 0u; t.es.r2 = t.es.r4 = t.es.r8 = 0xFFFFFFFFu; t.es.lastS = -1;
         t.ea = t.es;
-        for (int i = 0; i < 4; ++i) t.sm[i] = 0u;
+        for (int i = 0; i < 7; ++i) t.sm[i] = 0u;
     }
 }
 RB_HD void tight_leave(const TightState& t, LaneState& st) {
     st.x_prev = t.xp; st.x_cur = t.xc; st.xc.h = t.bh; st.xc.l = t.bl; st.lenL = t.lenL;
     st.cs = t.cs; st.ca = t.ca; st.es = t.es; st.ea = t.ea;
-    for (int i = 0; i < 4; ++i) st.sm[i] = t.sm[i];
+    for (int i = 0; i < 7; ++i) st.sm[i] = t.sm[i];
 }
 
 // ---- phase A: X_s[w+1] and the anchor word A_s[w] ---------------------------------------------------------------------
@@ -162,15 +172,25 @@ RB_HD uint32_t tight_anchor_full(const TightCfg& c, TightState& t, const PlaneWo
 
 // ---- phase B: window tests, component events, keep filter ---------------------------------------------------------------
 // an = A_{m-2} | A_{m-1} | A_{m+1} | A_{m+2}. Non-motif lanes produce all-zero masks.
+template <int TIER>
 RB_HD void tight_windows(const TightCfg& c, TightState& t, uint32_t an, uint32_t l1, uint32_t& passS, uint32_t& passA, uint32_t& cand) {
     const uint32_t x = t.xc;
+    const uint32_t o2p = t.cs.o2;
     passS = ~fail_ge2(x, l1, t.cs, cand) & c.mmask;
     passA = ~fail_ge3(x | an, t.ca) & c.mmask;
+    if (TIER != TIER_SMALL) {
+        // every perfect cutoff of these items is at least 18 (parse_perfect_shiftxor.cpp:193): only run ends that follow 16
+        // ones can be candidates, which leaves almost nothing for the exact check
+        const uint32_t o8 = ~(t.cs.o2 | fsl(o2p, t.cs.o2, 4));   // X_s[t-7..t] all ones
+        const uint32_t o16 = o8 & fsl(t.p8, o8, 8);
+        cand = ~x & fsl(t.p16, o16, 1);
+        t.p8 = o8; t.p16 = o16;
+    }
 }
 
 struct TightOut {
-    uint32_t x, s, el;  // surviving E bits, S mask of the word, E bits the prefilter elided
-    int last;           // position of the latest S bit in front of the word
+    uint32_t x, s, e;  // E bits that survived the prefilter, S mask of the word, all E bits
+    int last;          // position of the latest S bit in front of the word
 };
 template <int TIER>
 RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t passA, TightOut& o) {
@@ -179,14 +199,16 @@ RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t pas
     uint32_t v = fsl(sAp, sA, 1);
 #define RB_TSMEAR(i, d)                                  \
     {                                                    \
-        const uint32_t nv = v | fsl(t.sm[i], v, (d));   \
+        const uint32_t nv = v | fslc(t.sm[i], v, (d));  \
         t.sm[i] = v;                                     \
         v = nv;                                          \
     }
+    // every motif size of a MID / LARGE item has a cutoff of at least 16: the first four levels are plain doublings
     if (TIER == TIER_SMALL) { RB_TSMEAR(0, c.d0) RB_TSMEAR(1, c.d1) RB_TSMEAR(2, c.d2) RB_TSMEAR(3, c.d3) }
     else { RB_TSMEAR(0, 1) RB_TSMEAR(1, 2) RB_TSMEAR(2, 4) RB_TSMEAR(3, 8) }
+    RB_TSMEAR(4, c.d4) RB_TSMEAR(5, c.d5) RB_TSMEAR(6, c.d6)
 #undef RB_TSMEAR
-    o.x = eA & ~v; o.el = eA & v; o.s = sA; o.last = t.ea.lastS;
+    o.x = eA & ~v; o.e = eA; o.s = sA; o.last = t.ea.lastS;
     t.ea.lastS = sA ? p0 + 31 - clz32(sA) : t.ea.lastS;
 }
 RB_HD void tight_events_S(TightState& t, int p0, uint32_t passS, TightOut& o) {
@@ -194,7 +216,7 @@ RB_HD void tight_events_S(TightState& t, int p0, uint32_t passS, TightOut& o) {
     ev_step(passS, t.es, sS, eS, sSp);
     // a substitution component whose S bit is 9 or 10 back has length 8 or 9: below every cutoff
     o.x = eS & ~(fsl(sSp, sS, 9) | fsl(sSp, sS, 10));
-    o.el = eS & ~o.x; o.s = sS; o.last = t.es.lastS;
+    o.e = eS; o.s = sS; o.last = t.es.lastS;
     t.es.lastS = sS ? p0 + 31 - clz32(sS) : t.es.lastS;
 }
 // rotation at the end of a step

@@ -106,22 +106,28 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
         bool actS = false;
         for (int j = 0; j < bw; ++j) {
             const uint32_t an = pair[j >= 2 ? j - 2 : j] | pair[j + 1 < bw ? j + 1 : j];
-            tight_windows(tc[j], ts[j], an, l1[j], passS[j], passA[j], cand[j]);
+            tight_windows<TIER>(tc[j], ts[j], an, l1[j], passS[j], passA[j], cand[j]);
             tight_events_A<TIER>(tc[j], ts[j], 32 * w, passA[j], oa[j]);
             actS |= passS[j] != 0u;
         }
+        bool anyPS = false;
+        for (int j = 0; j < bw; ++j) { cand[j] &= tc[j].mmask; anyPS |= (cand[j] | passS[j]) != 0u; }
+        const bool runS = anyPS || zc < 2;
         for (int j = 0; j < bw; ++j) {
-            os[j].x = os[j].s = os[j].el = 0u; os[j].last = 0;
-            if (actS || zc < 2) tight_events_S(ts[j], 32 * w, passS[j], os[j]);
-            cand[j] &= tc[j].mmask;
+            os[j].x = os[j].s = os[j].e = 0u; os[j].last = 0;
+            if (runS) tight_events_S(ts[j], 32 * w, passS[j], os[j]);
+            // exact check of the survivors the bit-parallel filters do not decide
+            if (!tc[j].exactA && oa[j].x) oa[j].x = kept_exact(cut_anch(tc[j].s), 32 * w, oa[j].x, oa[j].s, oa[j].last);
+            if (tc[j].s > 30 && os[j].x) os[j].x = kept_exact(cut_subst(tc[j].s), 32 * w, os[j].x, os[j].s, os[j].last);
+            if (cand[j]) cand[j] = kept_exact_perfect(cw, w, tc[j].s, cut_perfect(tc[j].s), ts[j].xc, ts[j].xc & ~l1[j], cand[j]);
         }
-        if (actS || zc < 2) zc = actS ? 0 : zc + 1;
+        if (runS) zc = actS ? 0 : zc + 1;
         const uint32_t off = (uint32_t)io.raw.size();
         uint32_t elA = 0u, elS = 0u;
         for (int j = 0; j < bw; ++j) if (oa[j].x) io.raw.push_back(make_entry(STREAM_A, tc[j].s, oa[j].x, oa[j].s, oa[j].last));
         for (int j = 0; j < bw; ++j) if (cand[j]) io.raw.push_back(make_entry(STREAM_P, tc[j].s, cand[j], ts[j].xc & ~l1[j], 0));
         for (int j = 0; j < bw; ++j) if (os[j].x) io.raw.push_back(make_entry(STREAM_S, tc[j].s, os[j].x, os[j].s, os[j].last));
-        for (int j = 0; j < bw; ++j) { elA |= oa[j].el; elS |= os[j].el; }
+        for (int j = 0; j < bw; ++j) { elA |= oa[j].e & ~oa[j].x; elS |= os[j].e & ~os[j].x; }
         meta[w] = make_meta((int)(io.raw.size() - off), elS ? 32 - clz32(elS) : 0, elA ? 32 - clz32(elA) : 0, 0, off);
         for (int j = 0; j < bw; ++j) tight_rotate(ts[j], xn[j]);
         vprev = vcur; vcur = cw[w + 1].v;

@@ -50,3 +50,9 @@ def test_oracle_matches_reference_live_fuzz():
             synth.write_fasta(fa, [seq])
             contigs, _, rc = ou.ref_cp(fa, ["-m", mlo, "-M", mhi], stop_after_cp2=True)
         _check_cp1(ou.scan_events(seq, mlo, mhi), contigs[0]["cp1"], rc != 0)
+
+
+def test_integer_cutoff_formula_equals_the_reference_double_arithmetic():
+    """parse_anchored_shiftxor.cpp:572-573 computes int(0.9 * m) in double; the kernels use 9 * m // 10 (scan_core.h cut_anch)."""
+    for m in range(10, 2001):
+        assert int(0.9 * m) == (9 * m) // 10, m
