@@ -4,7 +4,7 @@
 
 Writes one row per candidate: contig, stream (P|S|A), start, end, mlen, flags, time — by default only the candidates
 that reach the consumer's length cutoff (flags 0 / NOCOMMIT); --all adds the DROPPED and PSEUDO bookkeeping records.
-For BED output use the drop-in program baseline/_ref/ribbit_gpu."""
+For BED output use the drop-in program ribbit_b200/bin/ribbit_gpu."""
 import argparse
 import os
 import sys

@@ -55,7 +55,7 @@ def build_oracle():
 
 
 def build_host():
-    """baseline/_ref/ribbit_gpu: the reference's host code (unmodified, from /root/reference) + the GPU processSequence.
+    """ribbit_b200/bin/ribbit_gpu: the reference's host code (unmodified, from /root/reference) + the GPU processSequence.
     Needs the reference sources, so it is only (re)built in the build container; the binary travels with the snapshot."""
     if os.path.isdir("/root/reference"):
         subprocess.run(["make", "-s", "-C", os.path.join(HERE, "host")], check=True)

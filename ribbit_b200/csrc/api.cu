@@ -33,6 +33,8 @@ struct rb_ctx {
     rb_params params{};
     BandLayout lay{};
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // rb_load_fasta: chunked H2D of the text, overlapped with the first kernel pass
+    cudaEvent_t copy_ev = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
@@ -312,6 +314,8 @@ void rb_destroy(rb_ctx* c) {
     if (c->h_long) cudaFreeHost(c->h_long);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->copy_ev) cudaEventDestroy(c->copy_ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -357,8 +361,23 @@ int rb_load_fasta(rb_ctx* c, const char* text, int64_t nbytes, int32_t* n_record
     if ((rc = ensure(c, c->d_ftiles, (size_t)std::max<long long>(nt, 1) * sizeof(int4)))) return rc;
     if ((rc = ensure(c, c->d_finfo, (size_t)std::max<long long>(nt, 1) * sizeof(longlong2)))) return rc;
     if ((rc = ensure(c, c->d_ftot, 2 * sizeof(long long)))) return rc;
-    if (nbytes > 0) RB_CUDA(c, cudaMemcpyAsync(c->d_text.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, st));
-    launch_fasta_count(c->d_text.p, nbytes, c->d_ftiles.p, c->d_finfo.p, (long long*)c->d_ftot.p, st);
+    // the text goes over in chunks on a second stream; pass 1 (per-tile summaries) of a chunk starts as soon as the chunk
+    // has arrived, while the next chunks are still on their way
+    if (!c->copy_stream) RB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->copy_ev) RB_CUDA(c, cudaEventCreateWithFlags(&c->copy_ev, cudaEventDisableTiming));
+    {
+        const long long chunk = 2048 * fasta_tile_bytes();  // 8 MiB
+        RB_CUDA(c, cudaEventRecord(c->copy_ev, st));         // the copies must not overtake earlier work on the text buffer
+        RB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev, 0));
+        for (long long at = 0; at < nbytes; at += chunk) {
+            const long long n = std::min<long long>(chunk, nbytes - at);
+            RB_CUDA(c, cudaMemcpyAsync((char*)c->d_text.p + at, text + at, (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
+            RB_CUDA(c, cudaEventRecord(c->copy_ev, c->copy_stream));
+            RB_CUDA(c, cudaStreamWaitEvent(st, c->copy_ev, 0));
+            launch_fasta_tiles(c->d_text.p, nbytes, at / fasta_tile_bytes(), (n + fasta_tile_bytes() - 1) / fasta_tile_bytes(), c->d_ftiles.p, st);
+        }
+    }
+    launch_fasta_scan(c->d_ftiles.p, nbytes, c->d_finfo.p, (long long*)c->d_ftot.p, st);
     RB_CUDA(c, cudaGetLastError());
     RB_CUDA(c, cudaMemcpyAsync(c->h_small, c->d_ftot.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     RB_CUDA(c, cudaStreamSynchronize(st));

@@ -89,10 +89,12 @@ __device__ __forceinline__ int block_excl_sum(int v, int* s_warp, int* total) {
 
 // tile summary: x = sequence-candidate bytes before the tile's first control byte, y = sequence bytes after it,
 // z = headers, w = line type at the tile's end (LT_NONE: no control byte in the tile)
-__global__ void __launch_bounds__(FT_THREADS) fasta_tile_kernel(const uint8_t* __restrict__ text, long long nbytes, int4* __restrict__ tiles) {
+__global__ void __launch_bounds__(FT_THREADS) fasta_tile_kernel(const uint8_t* __restrict__ text, long long nbytes, long long tile_first,
+                                                                int4* __restrict__ tiles) {
     __shared__ int s_warp[FT_THREADS / 32];
     __shared__ int s_sum[3];
-    const long long at = (long long)blockIdx.x * FT_TILE + (long long)threadIdx.x * FT_PER;
+    const long long tile = tile_first + blockIdx.x;
+    const long long at = tile * FT_TILE + (long long)threadIdx.x * FT_PER;
     const Slice d = load_slice(text, nbytes, at);
     if (threadIdx.x < 3) s_sum[threadIdx.x] = 0;
     int tile_last;
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(FT_THREADS) fasta_tile_kernel(const uint8_t* _
         if (nh) atomicAdd(&s_sum[2], nh);
     }
     __syncthreads();
-    if (threadIdx.x == 0) tiles[blockIdx.x] = make_int4(s_sum[0], s_sum[1], s_sum[2], tile_last < 0 ? LT_NONE : (tile_last & 1));
+    if (threadIdx.x == 0) tiles[tile] = make_int4(s_sum[0], s_sum[1], s_sum[2], tile_last < 0 ? LT_NONE : (tile_last & 1));
 }
 
 // One block. info[t] = {sequence bytes before tile t, headers before tile t | line type at its start << 40};
@@ -194,11 +196,15 @@ __global__ void __launch_bounds__(FT_THREADS) fasta_strip_kernel(const uint8_t* 
 
 long long fasta_tiles(long long nbytes) { return (nbytes + FT_TILE - 1) / FT_TILE; }
 
-void launch_fasta_count(const void* text, long long nbytes, void* tiles, void* info, long long* totals, cudaStream_t st) {
-    const long long nt = fasta_tiles(nbytes);
-    if (nt > 0) fasta_tile_kernel<<<(unsigned)nt, FT_THREADS, 0, st>>>((const uint8_t*)text, nbytes, (int4*)tiles);
-    fasta_scan_kernel<<<1, 1024, 0, st>>>((const int4*)tiles, nt, (longlong2*)info, totals);
+// pass 1 over the tiles [tile_first, tile_first + n_tiles): needs the text up to the end of these tiles on the device (and
+// the byte in front of them), so it can run while the rest of the file is still being copied
+void launch_fasta_tiles(const void* text, long long nbytes, long long tile_first, long long n_tiles, void* tiles, cudaStream_t st) {
+    if (n_tiles > 0) fasta_tile_kernel<<<(unsigned)n_tiles, FT_THREADS, 0, st>>>((const uint8_t*)text, nbytes, tile_first, (int4*)tiles);
 }
+void launch_fasta_scan(const void* tiles, long long nbytes, void* info, long long* totals, cudaStream_t st) {
+    fasta_scan_kernel<<<1, 1024, 0, st>>>((const int4*)tiles, fasta_tiles(nbytes), (longlong2*)info, totals);
+}
+long long fasta_tile_bytes() { return FT_TILE; }
 
 void launch_fasta_strip(const void* text, long long nbytes, const void* info, void* bases, long long* hdr_pos, long long* hdr_seq,
                         cudaStream_t st) {

@@ -333,7 +333,7 @@ __device__ __noinline__ void tight_run(TightIO* io) {
     q.pb = reinterpret_cast<const uint2*>(q.cw + (q.w + 1 + (q.c.s >> 5) + 1));
     q.mp = io->meta + q.w;
     q.cp = io->bcnt + q.w;
-    q.vprev = q.on ? q.cw[q.w - 1].v : 0xFFFFFFFFu; q.vcur = q.on ? q.cw[q.w].v : 0xFFFFFFFFu;
+    q.vprev = q.on ? v_eff(q.cw, q.w - 1) : 0xFFFFFFFFu; q.vcur = q.on ? q.cw[q.w].v : 0xFFFFFFFFu;
     // flags of the two words in front: unknown, so the first steps take the exact anchors; t.lenL is the general path's
     // carried run length
     q.flags = TF_SUSC | TF_SUSP | TF_PREV_RARE;
@@ -451,7 +451,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
     int Ha = warmup_anchor_words(q, H);
     lane_init(cfg, st, cw, q);
     int w = q;
-    int prev_slow = 1, fastrun = 0;
+    // (the keep filter's look-back is trusted after four fast words in a row; at the contig start there is nothing behind)
+    int prev_slow = 1, fastrun = q == 0 ? 3 : 0;
     uint32_t off = off0;  // raw-pool index of the next bucket's first slot
     if (j == 0) *cnt = 0;
     __syncwarp();
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
                     Ha = warmup_anchor_words(q, H);
                     lane_init(cfg, st, cw, q);
                     w = q;
-                    prev_slow = 1;
+                    prev_slow = 1; fastrun = q == 0 ? 3 : 0;
                     slow = 1;
                 }
             }
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             Ha = warmup_anchor_words(q, H);
             lane_init(cfg, st, cw, q);
             w = q;
-            prev_slow = 1;
+            prev_slow = 1; fastrun = q == 0 ? 3 : 0;
             ++restarts;
         } else if (active) {
             IterCtx it;
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
         // general path; the tight loop stops before the contig's tail zone (the anchor view differs from X_s there)
         const bool tight_ok = active && !badmask && w > we && w >= e0 && fastrun >= 4 && !prev_slow && !(b.debug & 1);
         const int wend = min(min(ch.w1, cg.nw - 1), ((L - b.lay.s_hi) >> 5) - 1);
-        const bool want = tight_ok && w < wend && (cw[w - 1].v & cw[w].v) == 0xFFFFFFFFu;
+        const bool want = tight_ok && w < wend && (v_eff(cw, w - 1) & cw[w].v) == 0xFFFFFFFFu;
         // every group with work must be able to enter, else the warp keeps to the general path for this word
         if (__any_sync(0xFFFFFFFFu, want) && __all_sync(0xFFFFFFFFu, want || !active)) {
             TightIO io;

@@ -70,7 +70,9 @@ void launch_motif_rows(const DevBatch& b, const void* seeds, const void* items, 
 // K0 (fasta_kernels.cu): FASTA text on the device -> sequence bytes + header table. tiles: int4[fasta_tiles], info:
 // longlong2[fasta_tiles], totals: {sequence bytes, headers} (device)
 long long fasta_tiles(long long nbytes);
-void launch_fasta_count(const void* text, long long nbytes, void* tiles, void* info, long long* totals, cudaStream_t st);
+void launch_fasta_tiles(const void* text, long long nbytes, long long tile_first, long long n_tiles, void* tiles, cudaStream_t st);
+void launch_fasta_scan(const void* tiles, long long nbytes, void* info, long long* totals, cudaStream_t st);
+long long fasta_tile_bytes();
 void launch_fasta_strip(const void* text, long long nbytes, const void* info, void* bases, long long* hdr_pos, long long* hdr_seq,
                         cudaStream_t st);
 // anchor planes A_s, s = s_lo .. s_lo+ns-1, of one contig: out[(s - s_lo) * nw + w]

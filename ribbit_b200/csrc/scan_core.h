@@ -389,11 +389,14 @@ struct LaneState {
 };
 enum : int { SYNC_X = 1, SYNC_P = 2, SYNC_S = 4, SYNC_A = 8, SYNC_ALL = 15 };
 
-// Word w is a FAST word when every window ending in words w-1 and w is evaluated (no N within reach, not at the
-// contig start) and w is not the last word of the contig; all other words are SLOW words and go through the
-// reference's state machines bit by bit. Warm-up words (before the first emitting word) are always processed slow.
+// Word w is a FAST word when every window ending in words w-1 and w is evaluated (no N within reach) and w is not the
+// last word of the contig; all other words are SLOW words and go through the reference's state machines bit by bit.
+// The contig start counts as evaluated: the windows that would end at positions 0..6 do not exist
+// (parse_substitute_shiftxor.cpp:469), which for the bit-parallel view is the same as failing windows with nothing but
+// failing windows in front of them (lane_init) - the fast path only has to mask them out of its pass words (v_eff).
+RB_HD uint32_t v_eff(const PlaneWord* cw, int w) { return cw[w].v | (w == 0 ? 0x7Fu : 0u); }
 RB_HD int word_is_fast(const PlaneWord* cw, int w, int nw) {
-    return cw[w].v == 0xFFFFFFFFu && cw[w - 1].v == 0xFFFFFFFFu && w != nw - 1;
+    return v_eff(cw, w) == 0xFFFFFFFFu && (w == 0 || v_eff(cw, w - 1) == 0xFFFFFFFFu) && w != nw - 1;
 }
 
 // Context of one lane iteration; the Sink receives the events.
@@ -717,8 +720,9 @@ RB_HD void lane_phase2_fast(Sink& sk, const LaneCfg& cfg, LaneState& st, const P
         const uint32_t l1 = fsl(st.x_prev, x, 1);
         const uint32_t b = x | a_m2 | a_m1 | a_p1 | a_p2;
         uint32_t cand;
-        const uint32_t passS = ~fail_ge2(x, l1, st.cs, cand);
-        const uint32_t passA = ~fail_ge3(b, st.ca);
+        const uint32_t vm = it.w == 0 ? cw[0].v : 0xFFFFFFFFu;  // the windows that would end at positions 0..6 do not exist
+        const uint32_t passS = ~fail_ge2(x, l1, st.cs, cand) & vm;
+        const uint32_t passA = ~fail_ge3(b, st.ca) & vm;
         uint32_t sS, eS, sSp, sA, eA, sAp;
         ev_step(passS, st.es, sS, eS, sSp);
         ev_step(passA, st.ea, sA, eA, sAp);

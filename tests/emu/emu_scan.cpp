@@ -76,7 +76,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
     TightState ts[32];
     TightCfg tc[32];
     for (int j = 0; j < bw; ++j) { tight_enter(cfg[j], st[j], ts[j]); tc[j] = make_tight_cfg(cfg[j]); }
-    uint32_t vprev = cw[w - 1].v, vcur = cw[w].v;
+    uint32_t vprev = v_eff(cw, w - 1), vcur = cw[w].v;
     bool susp = true, susc = true, prev_rare = true;
     int zc = 0;
     long steps = 0;
@@ -186,7 +186,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                 const int Ha = warmup_anchor_words(q, H);
                 for (int j = 0; j < lay.bw; ++j) lane_init(cfg[j], st[j], cw, q);
                 bool restart = false, replay = false;
-                int prev_slow = 1, fastrun = 0;
+                int prev_slow = 1, fastrun = q == 0 ? 3 : 0;
                 for (int w = q; w < ch.w1 && !restart;) {
                     const int lim = std::max(we, e0) - 2;  // no word is emitted before max(we, e0)
                     if (w >= q + Ha && w - 1 >= nb0) {
@@ -249,7 +249,7 @@ int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, in
                     // kernel couples the items of a warp only in WHEN it enters / leaves the loop and takes the rare paths
                     if (tight && w > we && w >= e0 && fastrun >= 4 && !prev_slow) {
                         const int wend = std::min(std::min(ch.w1, nw - 1), (((int)L - lay.s_hi) >> 5) - 1);
-                        if (w < wend && (cw[w - 1].v & cw[w].v) == 0xFFFFFFFFu) {
+                        if (w < wend && (v_eff(cw, w - 1) & cw[w].v) == 0xFFFFFFFFu) {
                             const int tier = tight_tier(band_m0(lay, band) - 2);
                             tight_steps += tier == TIER_SMALL ? run_tight<TIER_SMALL>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band])
                                          : tier == TIER_MID ? run_tight<TIER_MID>(lay, cfg, st, cw, w, wend, (int)L, io, meta[band])

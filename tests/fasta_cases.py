@@ -35,3 +35,9 @@ def random_fasta(rng, n_records, max_len, crlf=False):
     if rng.random() < 0.5 and text.endswith(b"\n"):
         text = text[:-1]
     return text
+
+
+def golden_random_texts():
+    """The 40 seeded random files behind tests/golden/golden_fasta.json (tests/golden/make_golden_fasta.py)."""
+    rng = np.random.default_rng(2031)
+    return [random_fasta(rng, int(rng.integers(1, 12)), int(rng.choice([50, 600, 5000])), crlf=(it % 7 == 3)) for it in range(40)]

@@ -31,7 +31,8 @@ def cut_anch(m):
 
 def fast_words(seq: bytes):
     """bool per word, as scan_core.h word_is_fast: every window ending in words w-1 and w is evaluated
-    (v[p] = p>=7 and no N in [p-7,p]) and w is not the last word of the contig."""
+    (v[p] = p>=7 and no N in [p-7,p]; positions 0..6 of the contig count as evaluated) and w is not the last word of the
+    contig."""
     L = len(seq)
     a = np.frombuffer(seq, dtype=np.uint8)
     isn = ~np.isin(a, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
@@ -42,10 +43,12 @@ def fast_words(seq: bytes):
     vv = np.zeros(nw * 32, dtype=bool)
     vv[:L] = v
     allv = vv.reshape(nw, 32).all(axis=1) if nw else np.zeros(0, dtype=bool)
+    # the contig start counts as evaluated (scan_core.h v_eff): the windows that would end at positions 0..6 do not exist
+    if nw:
+        allv[0] = bool(vv[7:32].all()) if L >= 32 else False
     fast = allv.copy()
     if nw:
         fast[1:] &= allv[:-1]
-        fast[0] = False
         fast[nw - 1] = False
     return fast
 

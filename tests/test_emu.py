@@ -109,3 +109,25 @@ def test_emulator_tiny_chunks_fuzz(seed):
         for cw in (1, 2, 3):
             got, _ = emu_util.emu_streams(seq, mlo, mhi, cw)
             _same(got, exp)
+
+
+@pytest.mark.parametrize("mlo,mhi", [(700, 900), (990, 1000)])
+def test_emulator_large_motif_sizes(mlo, mhi):
+    """Motif sizes up to the ABI's limit (max_mlen 1000): multi-word shifts, the keep filter beyond its exact range, contigs
+    only a few multiples of the shift long, N runs (the same cases run on the GPU in tests/test_gpu_parity.py)."""
+    rng = np.random.default_rng(mlo)
+    for case in range(4):
+        L = int(rng.choice([mhi + 5, 2 * mhi + 77, 5 * mhi, 9000]))
+        seq = bytearray(synth.fuzz_contig(rng, L, float(rng.choice([0, 0.001])), m_range=(2, 40)))
+        m = int(rng.integers(mlo, mhi + 1))
+        unit = bytes(synth.random_bases(rng, m))
+        k = min(L, int(rng.integers(2 * m, 4 * m)))
+        a = int(rng.integers(0, L - k + 1))
+        seq[a:a + k] = (unit * 5)[:k]
+        if case % 2:
+            q = int(rng.integers(0, L - 20)); seq[q:q + 20] = b"N" * 20
+        seq = bytes(seq)
+        exp = sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi))
+        for cw in (1 << 30, 7):
+            got, _ = emu_util.emu_streams(seq, mlo, mhi, cw)
+            _same(got, exp)

@@ -1,4 +1,4 @@
-"""End to end through the drop-in program baseline/_ref/ribbit_gpu (the reference's own main, merges, per-seed stage,
+"""End to end through the drop-in program ribbit_b200/bin/ribbit_gpu (the reference's own main, merges, per-seed stage,
 SSW and CIGAR code, with processSequence replaced by ribbit_b200/host/process_sequence_gpu.cpp + libribbit_scan.so):
 the merged seed lists (CP2) and the BED bytes must equal what the unmodified reference produced (golden vectors)."""
 import os
@@ -12,7 +12,7 @@ from ribbit_b200 import synth
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXE = os.path.join(ROOT, "baseline", "_ref", "ribbit_gpu")
+EXE = os.path.join(ROOT, "ribbit_b200", "bin", "ribbit_gpu")
 
 
 def _run(seq, mlo, mhi, extra=()):
@@ -27,7 +27,7 @@ def _run(seq, mlo, mhi, extra=()):
         return r.returncode, (open(bed, "rb").read() if os.path.exists(bed) else b""), lists, r.stderr
 
 
-@pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="baseline/_ref/ribbit_gpu is built in the build container (make -C ribbit_b200/host)")
+@pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="ribbit_b200/bin/ribbit_gpu is built in the build container (make -C ribbit_b200/host)")
 def test_bed_and_seed_lists_match_the_reference(golden):
     checked = 0
     for name, g in golden.items():
@@ -42,7 +42,7 @@ def test_bed_and_seed_lists_match_the_reference(golden):
     assert checked >= 14
 
 
-@pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="baseline/_ref/ribbit_gpu is built in the build container")
+@pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="ribbit_b200/bin/ribbit_gpu is built in the build container")
 def test_cli_flags_are_the_references(golden):
     # -p is accepted and ignored (the reference never reads it); missing -i is reported the reference's way
     g = golden["fuzz06"]
@@ -58,7 +58,7 @@ def _large_cases():
     return json.load(open(os.path.join(ROOT, "tests", "golden", "golden_large.json")))
 
 
-@pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="baseline/_ref/ribbit_gpu is built in the build container")
+@pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="ribbit_b200/bin/ribbit_gpu is built in the build container")
 @pytest.mark.parametrize("name", ["c1_1mbp_default", "c1_300k_l12", "c2_1mbp_nruns", "c4_500k_p070"])
 def test_mbp_scale_bed_digest_matches_the_reference(name):
     """BASELINE.json config shapes at 0.3-1 Mbp: md5 of the BED and of the merged seed lists vs the unmodified reference

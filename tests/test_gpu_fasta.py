@@ -43,6 +43,17 @@ def test_reader_quirks_on_device():
         check(sc, text)
 
 
+def test_device_reader_equals_the_reference_reader():
+    """rb_load_fasta against the records the unmodified reference read from the same bytes (golden_fasta.json)."""
+    from test_fasta import check_against_reference
+    sc = scan.Scanner(2, 6)
+
+    def fn(text):
+        names, lens = sc.load_fasta(text)
+        return names, lens.tolist()
+    assert check_against_reference(fn) > 100
+
+
 def test_random_fasta_files():
     rng = np.random.default_rng(2027)
     sc = scan.Scanner(2, 24)

@@ -224,12 +224,16 @@ def test_c5_shape_many_short_contigs(built):
     assert t["launches"] >= 4
 
 
-def test_c3_shape_multi_contig_batch_matches_single_scans(built):
-    """Several contigs of different sizes in one batch (configs[2] shape, scaled): identical to scanning each alone."""
-    contigs = [synth.contig_c2(L, seed=100 + i) for i, L in enumerate([600_000, 50_000, 1_200_000, 333_333])]
+def test_c3_shape_multi_contig_batch(built):
+    """Several contigs of different sizes in one batch (configs[2] shape, scaled): two of them against the oracle, all of
+    them identical to scanning each alone with another chunking."""
+    lengths = [600_000, 50_000, 1_200_000, 333_333]
+    contigs = [synth.contig_c2(L, seed=100 + i) for i, L in enumerate(lengths)]
     sc = scan.Scanner(2, 100)
     sc.load(contigs)
     res = sc.scan()
+    for i in (1, 3):
+        _same(scan.contig_streams(res, i), sm.expected_streams(contigs[i], ou.scan_events(contigs[i], 2, 100)), "contig %d" % i)
     for i, seq in enumerate(contigs):
         one = scan.Scanner(2, 100, chunk_words=211)
         one.load([seq])
@@ -239,6 +243,60 @@ def test_c3_shape_multi_contig_batch_matches_single_scans(built):
             assert len(a) == len(r1[s][0]) and (a == r1[s][0]).all(), (i, s)
         one.close()
     sc.close()
+
+
+FUZZ_RANGES = [(2, 100), (1, 6), (2, 24), (5, 30), (3, 10), (40, 100), (1, 100), (2, 8), (90, 100), (2, 150)]
+
+
+def fuzz_case(rng):
+    """One case of the fuzz campaigns (tools/fuzz_gpu.py, tools/fuzz_emu.py): contig lengths 1 .. 20 000, N densities up to
+    30 %, injected N runs and long repeats, ten motif ranges, chunk sizes 1 .. 64 words and automatic."""
+    L = int(rng.choice([1, 7, 8, 31, 32, 33, 63, 64, 65, 100, 500, 2000, 7000, 20000]))
+    nd = float(rng.choice([0, 0, 0.001, 0.01, 0.05, 0.3]))
+    mlo, mhi = FUZZ_RANGES[int(rng.integers(len(FUZZ_RANGES)))]
+    seq = synth.fuzz_contig(rng, L, nd, m_range=(mlo, min(mhi, 60)))
+    if rng.random() < 0.3 and L > 200:
+        b = bytearray(seq); a = int(rng.integers(0, L - 100)); k = int(rng.integers(50, min(3000, L - a)))
+        if rng.random() < 0.5:
+            b[a:a + k] = b"N" * k
+        else:
+            m = int(rng.integers(1, 40)); b[a:a + k] = (bytes(synth.random_bases(rng, m)) * (k // m + 1))[:k]
+        seq = bytes(b)
+    cw = int(rng.choice([0, 0, 1, 2, 3, 5, 17, 64]))
+    return seq, mlo, mhi, cw
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104])
+def test_fuzz_slice(built, seed):
+    """A deterministic slice (4 x 500 cases) of the campaign that found the round-1 state-conversion bug; the open-ended
+    campaigns stay in tools/."""
+    rng = np.random.default_rng(seed)
+    for n in range(500):
+        seq, mlo, mhi, cw = fuzz_case(rng)
+        got, _, _ = _scan_one(seq, mlo, mhi, cw)
+        _same(got, sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi)), "seed %d case %d (m %d-%d, cw %d, L %d)" % (seed, n, mlo, mhi, cw, len(seq)))
+
+
+@pytest.mark.parametrize("mlo,mhi", [(700, 900), (990, 1000), (300, 420)])
+def test_large_motif_sizes(built, mlo, mhi):
+    """Motif sizes up to the ABI's limit (rb_create: max_mlen <= 1000): multi-word shifts, guard = s_hi/32 + 5, keep filter
+    beyond its exact range (cutoffs above 96), contigs only a few multiples of the shift long, with N runs."""
+    rng = np.random.default_rng(mlo)
+    for case in range(6):
+        L = int(rng.choice([mhi + 5, 2 * mhi + 77, 5 * mhi, 9000]))
+        seq = bytearray(synth.fuzz_contig(rng, L, float(rng.choice([0, 0.001])), m_range=(2, 40)))
+        m = int(rng.integers(mlo, mhi + 1))          # a repeat of a motif size inside the range
+        unit = bytes(synth.random_bases(rng, m))
+        k = min(L, int(rng.integers(2 * m, 4 * m)))
+        a = int(rng.integers(0, L - k + 1))
+        seq[a:a + k] = (unit * 5)[:k]
+        if case % 2:
+            q = int(rng.integers(0, L - 20)); seq[q:q + 20] = b"N" * 20
+        seq = bytes(seq)
+        exp = sm.expected_streams(seq, ou.scan_events(seq, mlo, mhi))
+        for cw in (0, 7):
+            got, _, _ = _scan_one(seq, mlo, mhi, cw)
+            _same(got, exp, "m %d-%d case %d cw %d" % (mlo, mhi, case, cw))
 
 
 def test_full_size_c2_properties(built):

@@ -1,4 +1,4 @@
-"""Whole-program timing: the drop-in baseline/_ref/ribbit_gpu vs the unmodified reference oracle/_ref/ribbit_ref.
+"""Whole-program timing: the drop-in ribbit_b200/bin/ribbit_gpu vs the unmodified reference oracle/_ref/ribbit_ref.
 usage: python tools/exp_cli.py [bases] [c1|c2]; ribbit_gpu_hostmotif (make -C ribbit_b200/host HOST_MOTIF=1 BIN=...) = the drop-in
 without K7, if it was built."""
 import sys, os, time, subprocess, tempfile, hashlib
@@ -11,11 +11,11 @@ seq = synth.contig_c2(L, seed=21) if shape == 'c2' else synth.contig_c1(L, seed=
 with tempfile.TemporaryDirectory() as td:
     fa = os.path.join(td, "x.fa"); synth.write_fasta(fa, [seq])
     out = {}
-    arms = [("ribbit_gpu_nofilter", os.path.join(ROOT, "baseline/_ref/ribbit_gpu")), ("ribbit_gpu", os.path.join(ROOT, "baseline/_ref/ribbit_gpu"))]
+    arms = [("ribbit_gpu_nofilter", os.path.join(ROOT, "ribbit_b200/bin/ribbit_gpu")), ("ribbit_gpu", os.path.join(ROOT, "ribbit_b200/bin/ribbit_gpu"))]
     if os.environ.get("EXP_CLI_SKIP_NOFILTER"):
         arms = arms[1:]
-    if os.path.exists(os.path.join(ROOT, "baseline/_ref/ribbit_gpu_hostmotif")):
-        arms.append(("ribbit_gpu_hostmotif", os.path.join(ROOT, "baseline/_ref/ribbit_gpu_hostmotif")))
+    if os.path.exists(os.path.join(ROOT, "ribbit_b200/bin/ribbit_gpu_hostmotif")):
+        arms.append(("ribbit_gpu_hostmotif", os.path.join(ROOT, "ribbit_b200/bin/ribbit_gpu_hostmotif")))
     arms.append(("ribbit_ref", os.path.join(ROOT, "oracle/_ref/ribbit_ref")))
     for name, exe in arms:
         bed = os.path.join(td, name + ".bed")

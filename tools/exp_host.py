@@ -9,7 +9,7 @@ with tempfile.TemporaryDirectory() as td:
     fa = os.path.join(td, "x.fa"); synth.write_fasta(fa, [seq])
     for rep in range(2):
         t0 = time.perf_counter()
-        r = subprocess.run([os.path.join(ROOT, "baseline/_ref/ribbit_gpu"), "-i", fa, "-o", os.path.join(td, "o.bed")],
+        r = subprocess.run([os.path.join(ROOT, "ribbit_b200/bin/ribbit_gpu"), "-i", fa, "-o", os.path.join(td, "o.bed")],
                            env=dict(os.environ, RB_CP2_OUT="/dev/null", RB_CP_STOP_AFTER_CP2="1"), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         dt = time.perf_counter() - t0
         print("ribbit_gpu up to the merged seed lists: %.2f s (rc %d)" % (dt, r.returncode), "|", " ; ".join(l.split("\t")[0][:34] + " " + l.split("elapsed")[-1].strip(": ") for l in r.stderr.decode().split("\n") if "elapsed" in l), flush=True)

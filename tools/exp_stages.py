@@ -8,7 +8,7 @@ with tempfile.TemporaryDirectory() as td:
     fa = os.path.join(td, "x.fa"); synth.write_fasta(fa, [synth.contig_c2(L, seed=21)])
     for rep in range(2):
         t0 = time.perf_counter()
-        r = subprocess.run([os.path.join(ROOT, "baseline/_ref/ribbit_gpu"), "-i", fa, "-o", os.path.join(td, "o.bed")],
+        r = subprocess.run([os.path.join(ROOT, "ribbit_b200/bin/ribbit_gpu"), "-i", fa, "-o", os.path.join(td, "o.bed")],
                            env=dict(os.environ, RIBBIT_VERBOSE="1"), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         dt = time.perf_counter() - t0
         print("run %d: %.2f s total, rc %d" % (rep, dt, r.returncode))
