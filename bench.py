@@ -342,6 +342,7 @@ def run_gpu(args):
         sc.set_word_range(a, b)
         ctxs.append((sc, [c], (a, b)))
     int_peak = ctxs[0][0].int_peak() if ctxs else 0.0
+    int_peak_modes = ctxs[0][0].int_peak_modes() if ctxs and rank == 0 else None
 
     sampler = ClockSampler(local)
     sampler.start()                       # clocks under load: sampled from the warm-up steps to the end of the timed region
@@ -598,6 +599,7 @@ def run_gpu(args):
             "roofline": {"bound": "int", "kernel": "scan_kernel<32>", "achieved": achieved / 1e12, "peak": int_peak / 1e12,
                          "unit": "Tlaneop/s", "frac": achieved / int_peak if int_peak else None,
                          "note": "rank 0's share: algorithmic (12*NSHIFTS+39*NMOTIFS)/32 = %.1f word-ops per base x %d bases per launch / scan kernel time (CUDA events); peak = LOP3+SHF microbenchmark measured in this run; the HBM bound is ~100x looser" % (ops_per_base(M_LO, M_HI), my_bases),
+                         "peak_variants_tlaneops": {k: v / 1e12 for k, v in int_peak_modes.items()} if int_peak_modes else None,
                          "traffic": traffic,
                          "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "peak_source": "measured" if peaks else "fallback"}},

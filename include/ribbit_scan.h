@@ -45,7 +45,9 @@ typedef struct rb_params {
     int32_t min_mlen;     /* >= 1 */
     int32_t max_mlen;     /* >= min_mlen, <= 1000 */
     int32_t chunk_words;  /* 0 = automatic; words (32 bases) of a contig scanned by one warp item */
-    int32_t reserved;     /* must be 0 */
+    int32_t reserved;     /* diagnostic switches, 0 in production: bit 0 = never enter the tight loop, bit 1 = do not skip
+                           * chunks that lie inside an N run. Both only change which code path computes the (identical)
+                           * result; values above 3 are rejected (RB_E_ARG) */
 } rb_params;
 
 /* One candidate record of a stream.
@@ -186,6 +188,13 @@ int rb_get_timing(const rb_ctx *ctx, rb_timing *out);
 /* Diagnostic for the roofline: LOP3 + funnel-shift operations per second (32 lanes counted per warp instruction)
  * this GPU sustains, measured with a register-only microbenchmark of the scan's instruction mix. */
 int rb_measure_int_peak(rb_ctx *ctx, double *ops_per_s);
+/* The same microbenchmark with four instruction mixes: [0] funnel shifts + LOP3 (= rb_measure_int_peak), [1] LOP3 only,
+ * [2] funnel shifts only, [3] LOP3 + IMAD (logic pipe and multiply-add pipe together). */
+int rb_measure_int_peak_modes(rb_ctx *ctx, double ops_per_s[4]);
+/* Diagnostic: per (chunk, motif band) work item of the scan kernel {start ns, end ns, words through the general path,
+ * warm-up restarts << 32 | bit-serial words}. The first call switches the recording on (returns RB_E_STATE); call again
+ * after the next rb_scan_device. */
+int rb_debug_item_clocks(rb_ctx *ctx, int64_t *out, int64_t capacity_items, int64_t *n_items);
 
 /* K5 — the per-seed gate of processSeed / processSeedMotifWise (parse_seed.cpp:344-367,
  * parse_smallmotif_seed.cpp:216-235), batched: for each seed (contig, start, end, mlen), end <= L (the merges clamp seeds to

@@ -241,7 +241,7 @@ int finish_load(rb_ctx* c, const void* ascii_dev, int32_t n) {
     if ((rc = ensure(c, c->d_meta, (size_t)b.n_buckets * c->lay.nbands * sizeof(Meta)))) return rc;
     if ((rc = ensure(c, c->d_bcnt, (size_t)std::max<long long>(b.n_buckets, 1) * c->lay.nbands * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(c, c->d_counters, 4 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->d_partial, ((size_t)b.n_merge_blocks + 1) * sizeof(BlockPartial)))) return rc;
+    if ((rc = ensure(c, c->d_partial, ((size_t)b.n_merge_blocks + 2 + (size_t)b.n_merge_blocks / MERGE_SEG + 1) * sizeof(BlockPartial)))) return rc;
     if ((rc = ensure(c, c->d_contig_off, 3 * ((size_t)n + 1) * sizeof(long long)))) return rc;
     if ((rc = ensure(c, c->d_totals, 3 * sizeof(long long)))) return rc;
     b.ascii = (const uint8_t*)ascii_dev;
@@ -499,7 +499,7 @@ int rb_scan_device(rb_ctx* c) {
         if (attempt == 0) RB_CUDA(c, cudaEventRecord(c->ev[2], st));
         launch_merge_count(b, st);
         launch_merge_write(b, st);
-        tm.launches += b.n_buckets ? 3 : 0;
+        tm.launches += b.n_buckets ? 4 : 0;
         RB_CUDA(c, cudaEventRecord(c->ev[3], st));
         RB_CUDA(c, cudaMemcpyAsync(c->h_small, b.totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
         RB_CUDA(c, cudaMemcpyAsync(c->h_small + 4, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -709,6 +709,19 @@ int rb_measure_int_peak(rb_ctx* c, double* ops_per_s) {
     int rc = ensure(c, c->d_counters, 4 * sizeof(int));
     if (rc) return rc;
     *ops_per_s = measure_int_peak(c->stream, (uint32_t*)c->d_counters.p, sms);
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RB_CUDA(c, cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_measure_int_peak_modes(rb_ctx* c, double ops_per_s[4]) {
+    if (!c || !ops_per_s) return RB_E_ARG;
+    RB_CUDA(c, cudaSetDevice(c->device));
+    int sms = 0;
+    RB_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    int rc = ensure(c, c->d_counters, 4 * sizeof(int));
+    if (rc) return rc;
+    measure_int_peak_modes(c->stream, (uint32_t*)c->d_counters.p, sms, ops_per_s);
     RB_CUDA(c, cudaStreamSynchronize(c->stream));
     RB_CUDA(c, cudaGetLastError());
     return RB_OK;

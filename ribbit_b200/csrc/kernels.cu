@@ -729,16 +729,20 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_count_kernel(DevBatch b) {
     }
 }
 
-// one block: every thread owns a contiguous range of the block partials (local prefix), one block-wide scan of the
-// per-thread totals, then the exclusive prefixes are written back; entry n_merge_blocks receives the totals
-__global__ void __launch_bounds__(1024) merge_scan_kernel(DevBatch b) {
+// Exclusive prefix (three sums, two maxima) over segments of `seg` partials, one block per segment: every thread owns a
+// contiguous range (local prefix), one block-wide scan of the per-thread totals, then the exclusive prefixes are written
+// back in place; seg_total[segment] receives the segment's total (and `totals` the three sums when given).
+// Two levels: the per-block partials in segments of MERGE_SEG, then the segment totals in one block.
+__global__ void __launch_bounds__(1024) merge_scan_kernel(BlockPartial* __restrict__ arr, int n, int seg, BlockPartial* __restrict__ seg_total,
+                                                          long long* __restrict__ totals) {
     __shared__ unsigned long long s_w[5][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = (b.n_merge_blocks + 1023) / 1024;
-    const int i0 = threadIdx.x * per, i1 = min(b.n_merge_blocks, i0 + per);
+    const int s0 = blockIdx.x * seg, s1 = min(n, s0 + seg);
+    const int per = (seg + 1023) / 1024;
+    const int i0 = min(s1, s0 + (int)threadIdx.x * per), i1 = min(s1, i0 + per);
     unsigned long long v[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
     for (int i = i0; i < i1; ++i) {
-        const BlockPartial p = b.partial[i];
+        const BlockPartial p = arr[i];
         v[0] += p.sum[0]; v[1] += p.sum[1]; v[2] += p.sum[2];
         v[3] = umax64(v[3], p.emax[0]); v[4] = umax64(v[4], p.emax[1]);
     }
@@ -765,19 +769,27 @@ __global__ void __launch_bounds__(1024) merge_scan_kernel(DevBatch b) {
         all[k] = tot;
     }
     for (int i = i0; i < i1; ++i) {  // exclusive prefix of every partial of this thread's range
-        const BlockPartial p = b.partial[i];
+        const BlockPartial p = arr[i];
         BlockPartial o;
         o.sum[0] = ex[0]; o.sum[1] = ex[1]; o.sum[2] = ex[2]; o.emax[0] = ex[3]; o.emax[1] = ex[4];
-        b.partial[i] = o;
+        arr[i] = o;
         ex[0] += p.sum[0]; ex[1] += p.sum[1]; ex[2] += p.sum[2];
         ex[3] = umax64(ex[3], p.emax[0]); ex[4] = umax64(ex[4], p.emax[1]);
     }
     if (threadIdx.x == 0) {
         BlockPartial p;
         p.sum[0] = all[0]; p.sum[1] = all[1]; p.sum[2] = all[2]; p.emax[0] = all[3]; p.emax[1] = all[4];
-        b.partial[b.n_merge_blocks] = p;
-        b.totals[0] = (long long)all[0]; b.totals[1] = (long long)all[1]; b.totals[2] = (long long)all[2];
+        seg_total[blockIdx.x] = p;
+        if (totals) { totals[0] = (long long)all[0]; totals[1] = (long long)all[1]; totals[2] = (long long)all[2]; }
     }
+}
+// the partial of merge block `blk` after both levels: its prefix inside the segment combined with the segment's prefix
+__device__ __forceinline__ BlockPartial merge_block_prefix(const DevBatch& b, int blk) {
+    BlockPartial p = b.partial[blk];
+    const BlockPartial g = b.partial[b.n_merge_blocks + 1 + blk / MERGE_SEG];
+    for (int s = 0; s < 3; ++s) p.sum[s] += g.sum[s];
+    p.emax[0] = umax64(p.emax[0], g.emax[0]); p.emax[1] = umax64(p.emax[1], g.emax[1]);
+    return p;
 }
 
 // Phase 1 (thread = bucket): stream offsets of every bucket of the block, pseudo records, per-contig offsets.
@@ -793,6 +805,8 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     __shared__ int s_w[MERGE_BLOCK];
     __shared__ int s_c[MERGE_BLOCK];
     __shared__ uint32_t s_wsum[MERGE_BLOCK / 32];
+    __shared__ uint32_t s_x[MERGE_STAGE], s_z[MERGE_STAGE];
+    __shared__ unsigned char s_bk_of[MERGE_STAGE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long gb = b.gb_first + (long long)blockIdx.x * MERGE_BLOCK + tid;
     const bool live = gb < b.gb_first + b.n_active;
@@ -819,7 +833,7 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     unsigned xs[3], tot[3];
     unsigned long long xe[2], tote[2];
     block_scan(bi.n, bi.emax, xs, xe, tot, tote);
-    const BlockPartial bp = b.partial[blockIdx.x];
+    const BlockPartial bp = merge_block_prefix(b, (int)blockIdx.x);
     const BlockPartial total = b.partial[b.n_merge_blocks];
     const long long sbase[3] = {0ll, (long long)total.sum[0], (long long)(total.sum[0] + total.sum[1])};
     // block prefix of the raw slot counts
@@ -853,7 +867,10 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
     }
     __syncthreads();
 
+    // The slots of the block are staged in shared memory once (mask / key word, mflags, bucket): the rank loops then run
+    // on shared memory. A block with more slots than fit ranks from global memory.
     const uint32_t T = s_pre[MERGE_BLOCK];
+    const bool staged = T <= MERGE_STAGE;
     for (uint32_t r = tid; r < T; r += MERGE_BLOCK) {
         int lo = 0, hi = MERGE_BLOCK - 1;  // largest bucket with s_pre[bucket] <= r
         while (lo < hi) {
@@ -865,27 +882,79 @@ __global__ void __launch_bounds__(MERGE_BLOCK) merge_write_kernel(DevBatch b) {
         int band = 0;
         while (idx >= s_n[band][bk]) { idx -= s_n[band][bk]; ++band; }
         const int4 v = *reinterpret_cast<const int4*>(b.raw + s_off[band][bk] + idx);
-        const int st = (v.z >> REC_STREAM_SHIFT) & 3;
-        const bool is_entry = ((v.z >> 16) & REC_ENTRY) != 0;
-        const int w = s_w[bk], mlen = v.z & 0xFFFF;
+        if (staged) {
+            // what ranking needs of a slot: the kept mask (entry) or the key (record), and mflags
+            s_x[r] = ((v.z >> 16) & REC_ENTRY) ? (uint32_t)v.x : (uint32_t)v.w;
+            s_z[r] = (uint32_t)v.z;
+        }
+        s_bk_of[r < MERGE_STAGE ? r : 0] = (unsigned char)bk;
+        if (!staged) {
+            // (rare) rank from global memory
+            const int st = (v.z >> REC_STREAM_SHIFT) & 3;
+            const bool is_entry = ((v.z >> 16) & REC_ENTRY) != 0;
+            const int w = s_w[bk], mlen = v.z & 0xFFFF;
+            const long long dbase = sbase[st] + (long long)bp.sum[st] + s_dst[st][bk];
+            const uint32_t mk = (uint32_t)mlen << 2;
+            for (uint32_t bits = is_entry ? (uint32_t)v.x : 1u; bits; bits &= bits - 1u) {
+                const int i = __ffs((int)bits) - 1;
+                const uint32_t key = is_entry ? (((uint32_t)i << 18) | mk) : (uint32_t)v.w;
+                const int ki = (int)(key >> 18);
+                const uint32_t lowkey = key & 0x3FFFFu;
+                int rank = 0;
+                for (int k = 0; k < nbands; ++k) {
+                    const int n = s_n[k][bk];
+                    const int4* q = reinterpret_cast<const int4*>(b.raw + s_off[k][bk]);
+                    for (int u = 0; u < n; ++u) {
+                        const int4 ov = q[u];
+                        if (((ov.z >> REC_STREAM_SHIFT) & 3) != st) continue;
+                        if ((ov.z >> 16) & REC_ENTRY) rank += __popc((uint32_t)ov.x & lowmask(ki + ((((uint32_t)(ov.z & 0xFFFF)) << 2) < lowkey ? 1 : 0)));
+                        else rank += (uint32_t)ov.w < key ? 1 : 0;
+                    }
+                }
+                int4 out;
+                if (is_entry) {
+                    Rec e;
+                    e.start = v.x; e.end = v.y; e.mflags = v.z; e.key = v.w;
+                    int s0, e0;
+                    entry_interval(e, w, b.planes + b.contigs[s_c[bk]].word_base, i, s0, e0);
+                    out = make_int4(s0, e0, mlen, 32 * w + i);
+                } else {
+                    out = make_int4(v.x, v.y, v.z & ((1 << REC_STREAM_SHIFT) - 1), 32 * w + (v.w >> 18));
+                }
+                const long long at = dbase + rank;
+                if (at < b.dst_cap) *reinterpret_cast<int4*>(b.dst + at) = out;
+            }
+        }
+    }
+    if (!staged) return;
+    __syncthreads();
+    for (uint32_t r = tid; r < T; r += MERGE_BLOCK) {
+        const int bk = s_bk_of[r];
+        uint32_t idx = r - s_pre[bk];
+        int band = 0;
+        while (idx >= s_n[band][bk]) { idx -= s_n[band][bk]; ++band; }
+        const uint32_t z = s_z[r];
+        const int st = (int)(z >> REC_STREAM_SHIFT) & 3;
+        const bool is_entry = ((z >> 16) & REC_ENTRY) != 0;
+        const int w = s_w[bk], mlen = (int)(z & 0xFFFF);
         const long long dbase = sbase[st] + (long long)bp.sum[st] + s_dst[st][bk];
         const uint32_t mk = (uint32_t)mlen << 2;
-        for (uint32_t bits = is_entry ? (uint32_t)v.x : 1u; bits; bits &= bits - 1u) {
+        const uint32_t r0 = s_pre[bk], r1 = s_pre[bk + 1];
+        int4 v = make_int4(0, 0, 0, 0);
+        bool have = false;
+        for (uint32_t bits = is_entry ? s_x[r] : 1u; bits; bits &= bits - 1u) {
             const int i = __ffs((int)bits) - 1;
-            const uint32_t key = is_entry ? (((uint32_t)i << 18) | mk) : (uint32_t)v.w;
+            const uint32_t key = is_entry ? (((uint32_t)i << 18) | mk) : s_x[r];
             const int ki = (int)(key >> 18);
             const uint32_t lowkey = key & 0x3FFFFu;
             int rank = 0;
-            for (int k = 0; k < nbands; ++k) {
-                const int n = s_n[k][bk];
-                const int4* q = reinterpret_cast<const int4*>(b.raw + s_off[k][bk]);
-                for (int u = 0; u < n; ++u) {
-                    const int4 ov = q[u];
-                    if (((ov.z >> REC_STREAM_SHIFT) & 3) != st) continue;
-                    if ((ov.z >> 16) & REC_ENTRY) rank += __popc((uint32_t)ov.x & lowmask(ki + ((((uint32_t)(ov.z & 0xFFFF)) << 2) < lowkey ? 1 : 0)));
-                    else rank += (uint32_t)ov.w < key ? 1 : 0;
-                }
+            for (uint32_t u = r0; u < r1; ++u) {
+                const uint32_t oz = s_z[u];
+                if (((oz >> REC_STREAM_SHIFT) & 3) != (uint32_t)st) continue;
+                if ((oz >> 16) & REC_ENTRY) rank += __popc(s_x[u] & lowmask(ki + (((oz & 0xFFFFu) << 2) < lowkey ? 1 : 0)));
+                else rank += s_x[u] < key ? 1 : 0;
             }
+            if (!have) { v = *reinterpret_cast<const int4*>(b.raw + s_off[band][bk] + idx); have = true; }  // the other fields
             int4 out;
             if (is_entry) {
                 Rec e;
@@ -940,7 +1009,11 @@ void launch_compact(const Rec* src, long long n, long long b1, long long b2, voi
 void launch_merge_count(const DevBatch& b, cudaStream_t st) {
     if (b.n_buckets == 0) return;
     merge_count_kernel<<<(unsigned)b.n_merge_blocks, MERGE_BLOCK, 0, st>>>(b);
-    merge_scan_kernel<<<1, 1024, 0, st>>>(b);
+    // partial[0 .. n) = per-block sums, partial[n] = grand total, partial[n + 1 ..] = segment prefixes
+    const int nseg = (b.n_merge_blocks + MERGE_SEG - 1) / MERGE_SEG;
+    BlockPartial* segs = b.partial + b.n_merge_blocks + 1;
+    merge_scan_kernel<<<(unsigned)nseg, 1024, 0, st>>>(b.partial, b.n_merge_blocks, MERGE_SEG, segs, nullptr);
+    merge_scan_kernel<<<1, 1024, 0, st>>>(segs, nseg, nseg, b.partial + b.n_merge_blocks, b.totals);
 }
 void launch_merge_write(const DevBatch& b, cudaStream_t st) {
     if (b.n_buckets == 0) return;
@@ -1037,31 +1110,50 @@ void launch_anchor_planes(const PlaneWord* cw, int L, int nw, int s_lo, int ns, 
 // Integer-pipe microbenchmark (roofline denominator of the scan): independent chains of funnel shifts and LOP3s,
 // the instruction mix of the bit-sliced scan. 16 ops per thread per inner step.
 // ---------------------------------------------------------------------------------------------------------------
+// MODE 0: funnel shifts and LOP3s alternating (the mix of the bit-sliced scan), 1: LOP3 only, 2: funnel shifts only,
+// 3: LOP3 alternating with IMAD (a multiply-add on the FMA pipe: shows what the second integer pipe adds)
+template <int MODE>
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, uint32_t k) {
     uint32_t a0 = threadIdx.x, a1 = blockIdx.x, a2 = a0 * 3u + 1u, a3 = a1 * 5u + 2u, a4 = a0 ^ 0x55u, a5 = a1 ^ 0xAAu,
              a6 = a0 + 77u, a7 = a1 + 99u;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            a0 = __funnelshift_r(a0, a1, 7); a1 = (a1 & k) ^ a2;
-            a2 = __funnelshift_r(a2, a3, 9); a3 = (a3 | k) ^ a4;
-            a4 = __funnelshift_r(a4, a5, 11); a5 = (a5 & k) ^ a6;
-            a6 = __funnelshift_r(a6, a7, 13); a7 = (a7 | k) ^ a0;
+            if (MODE == 0) {
+                a0 = __funnelshift_r(a0, a1, 7); a1 = (a1 & k) ^ a2;
+                a2 = __funnelshift_r(a2, a3, 9); a3 = (a3 | k) ^ a4;
+                a4 = __funnelshift_r(a4, a5, 11); a5 = (a5 & k) ^ a6;
+                a6 = __funnelshift_r(a6, a7, 13); a7 = (a7 | k) ^ a0;
+            } else if (MODE == 1) {
+                a0 = (a0 | k) ^ a1; a1 = (a1 & k) ^ a2; a2 = (a2 | k) ^ a3; a3 = (a3 & k) ^ a4;
+                a4 = (a4 | k) ^ a5; a5 = (a5 & k) ^ a6; a6 = (a6 | k) ^ a7; a7 = (a7 & k) ^ a0;
+            } else if (MODE == 2) {
+                a0 = __funnelshift_r(a0, a1, 7); a1 = __funnelshift_r(a1, a2, 5);
+                a2 = __funnelshift_r(a2, a3, 9); a3 = __funnelshift_r(a3, a4, 3);
+                a4 = __funnelshift_r(a4, a5, 11); a5 = __funnelshift_r(a5, a6, 2);
+                a6 = __funnelshift_r(a6, a7, 13); a7 = __funnelshift_r(a7, a0, 6);
+            } else {
+                a0 = a0 * k + a1; a1 = (a1 & k) ^ a2;
+                a2 = a2 * k + a3; a3 = (a3 | k) ^ a4;
+                a4 = a4 * k + a5; a5 = (a5 & k) ^ a6;
+                a6 = a6 * k + a7; a7 = (a7 | k) ^ a0;
+            }
         }
     }
     const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
     if (r == 0x12345678u) out[0] = r;
 }
 
-double measure_int_peak(cudaStream_t st, uint32_t* scratch, int sms) {
+template <int MODE>
+static double measure_mode(cudaStream_t st, uint32_t* scratch, int sms) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int blocks = sms * 8, iters = 4096;
-    int_peak_kernel<<<blocks, 256, 0, st>>>(scratch, 64, 0x0F0F0F0Fu);
+    int_peak_kernel<MODE><<<blocks, 256, 0, st>>>(scratch, 64, 0x0F0F0F0Fu);
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0, st);
-        int_peak_kernel<<<blocks, 256, 0, st>>>(scratch, iters, 0x0F0F0F0Fu);
+        int_peak_kernel<MODE><<<blocks, 256, 0, st>>>(scratch, iters, 0x0F0F0F0Fu);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0.f;
@@ -1071,6 +1163,14 @@ double measure_int_peak(cudaStream_t st, uint32_t* scratch, int sms) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double ops = (double)blocks * 256.0 * iters * 32.0;
     return ops / (best * 1e-3);
+}
+
+double measure_int_peak(cudaStream_t st, uint32_t* scratch, int sms) { return measure_mode<0>(st, scratch, sms); }
+void measure_int_peak_modes(cudaStream_t st, uint32_t* scratch, int sms, double out[4]) {
+    out[0] = measure_mode<0>(st, scratch, sms);
+    out[1] = measure_mode<1>(st, scratch, sms);
+    out[2] = measure_mode<2>(st, scratch, sms);
+    out[3] = measure_mode<3>(st, scratch, sms);
 }
 
 }  // namespace rb

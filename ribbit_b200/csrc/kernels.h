@@ -44,7 +44,8 @@ struct DevBatch {
     long long* item_clk;            // diagnostics (rb_debug_item_clocks): [n_items][2] start / end of the item in globaltimer ns, or null
     int* counters;                  // [0] overflowed items, [1] warm-up restarts, [2] a count field overflowed (error)
     // merge
-    BlockPartial* partial;          // [n_merge_blocks + 1]; after M2: exclusive prefixes, last = totals
+    BlockPartial* partial;          // [n_merge_blocks + 1 + segments]; after M2: exclusive prefixes inside the segment, [n] = totals,
+                                    //   then the segments' exclusive prefixes
     int n_merge_blocks;
     Rec* dst;                       // final pool: stream P, then S, then A
     long long dst_cap;              // records the final pool holds (writes beyond it are dropped: the host re-runs M3)
@@ -53,6 +54,8 @@ struct DevBatch {
 };
 
 static const int MERGE_BLOCK = 256;
+static const int MERGE_STAGE = 2560;  // slots of a merge block staged in shared memory (M3)
+static const int MERGE_SEG = 4096;   // merge blocks per segment of the two-level prefix (M2)
 
 void launch_pack(const DevBatch& b, cudaStream_t st);
 void launch_scan(const DevBatch& b, cudaStream_t st);
@@ -79,6 +82,8 @@ void launch_fasta_strip(const void* text, long long nbytes, const void* info, vo
 void launch_anchor_planes(const PlaneWord* cw, int L, int nw, int s_lo, int ns, uint32_t* out, cudaStream_t st);
 // LOP3 + SHF warp-lane operations per second the device sustains (integer-pipe roofline denominator)
 double measure_int_peak(cudaStream_t st, uint32_t* scratch, int sms);
+// the same for four instruction mixes: {SHF + LOP3, LOP3 only, SHF only, LOP3 + IMAD}
+void measure_int_peak_modes(cudaStream_t st, uint32_t* scratch, int sms, double out[4]);
 
 }  // namespace rb
 #endif

@@ -22,7 +22,7 @@ STREAM_NAMES = ("perfect", "subst", "anchored")
 
 EXPORTS = ("rb_abi_version", "rb_create", "rb_destroy", "rb_last_error", "rb_load_contigs", "rb_load_contigs_device",
            "rb_scan_device", "rb_fetch", "rb_scan", "rb_counts", "rb_get_timing", "rb_filter_seeds", "rb_get_planes",
-           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact", "rb_motif_rows", "rb_load_fasta", "rb_fasta_records", "rb_set_word_range", "rb_get_elided_max")
+           "rb_measure_int_peak", "rb_get_anchor_planes", "rb_fetch_compact", "rb_motif_rows", "rb_load_fasta", "rb_fasta_records", "rb_set_word_range", "rb_get_elided_max", "rb_measure_int_peak_modes", "rb_debug_item_clocks")
 
 
 FASTA_REC_DTYPE = np.dtype([("name_off", "<i8"), ("name_len", "<i4"), ("length", "<i4")])
@@ -110,6 +110,10 @@ def load_library(path=LIB_PATH):
     lib.rb_motif_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.rb_measure_int_peak.restype = ctypes.c_int
     lib.rb_measure_int_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    lib.rb_measure_int_peak_modes.restype = ctypes.c_int
+    lib.rb_measure_int_peak_modes.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    lib.rb_debug_item_clocks.restype = ctypes.c_int
+    lib.rb_debug_item_clocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     lib.rb_get_anchor_planes.restype = ctypes.c_int
     lib.rb_get_anchor_planes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     lib.rb_get_planes.restype = ctypes.c_int
@@ -266,6 +270,12 @@ class Scanner:
         v = ctypes.c_double()
         self._check(self.lib.rb_measure_int_peak(self.ctx, ctypes.byref(v)))
         return v.value
+
+    def int_peak_modes(self):
+        """Measured lane-operations per second for {SHF + LOP3, LOP3 only, SHF only, LOP3 + IMAD}."""
+        v = (ctypes.c_double * 4)()
+        self._check(self.lib.rb_measure_int_peak_modes(self.ctx, v))
+        return {"shf_lop3": v[0], "lop3": v[1], "shf": v[2], "lop3_imad": v[3]}
 
     def planes(self, contig):
         nw = (int(self.lengths[contig]) + 31) // 32
