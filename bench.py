@@ -450,7 +450,7 @@ def run_gpu(args):
     # ribbit_b200.pipeline.ScanPipeline one by one: three contexts on the GPU, so the copies of one contig overlap the
     # kernels of the next. All results of all K steps are complete inside the timed region.
     units = [(c, None) for c in whole] + [(c, (a, b)) for c, a, b in ranges]
-    pipe = pipeline.ScanPipeline(M_LO, M_HI, device=local, depth=3, compact=True)
+    pipe = pipeline.ScanPipeline(M_LO, M_HI, device=local, depth=args.depth, compact=True)
 
     def submit_all():
         return [pipe.submit_flat(host_np[offs[c]:offs[c] + lengths[c] + 1], [lengths[c]], rng) for c, rng in units]
@@ -591,7 +591,7 @@ def run_gpu(args):
                        "input_generation_s": gen_s, "also": also},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "per step and contig: rb_load_contigs (pinned host ASCII -> HBM) + rb_scan_device (kernels) + rb_fetch_compact (D2H of the three streams as 8-byte records); contigs pipelined over 3 contexts per GPU (ribbit_b200.pipeline)",
+                    "what": "per step and contig: rb_load_contigs (pinned host ASCII -> HBM) + rb_scan_device (kernels) + rb_fetch_compact (D2H of the three streams as 8-byte records); contigs pipelined over %d contexts per GPU (ribbit_b200.pipeline)" % args.depth,
                     "pcie_gbs_per_direction": pcie_each,
                     "pcie_ceiling_gbps": world * min(pcie_each * 1e9 / (h2d / genome), pcie_each * 1e9 / (d2h / genome)) / 1e9 if h2d and d2h else None,
                     "pcie_note": "plain cudaMemcpyAsync of 1 GiB pinned buffers, H2D and D2H at the same time, all ranks at once; ceiling = that rate over the bytes per base each direction moves"},
@@ -621,6 +621,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scale of the C3 contig lengths (1.0 = 3.1 Gbp; the parity gate needs 1.0)")
     ap.add_argument("--no-gate", action="store_true", help="skip the parity gate (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip C2 / C5 / K0 / K7 / CPU-baseline legs (profiling runs)")
+    ap.add_argument("--depth", type=int, default=4, help="scan contexts per GPU in the end-to-end pipeline")
     ap.add_argument("--c5-contigs", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="bases per CPU-baseline process")
     ap.add_argument("--ref-sample", type=int, default=500_000, help="bases per process and step for --impl reference")
