@@ -48,6 +48,18 @@ def build_emulator(force=False):
     return EMU
 
 
+MERGE = os.path.join(ROOT, "tests", "emu", "libseedmerge.so")
+
+
+def build_merge(force=False):
+    """The host seed-list merges (ribbit_b200/host/seed_merge.cpp) as a library of their own, for the tests."""
+    src = os.path.join(HERE, "host", "seed_merge.cpp")
+    if not force and not _newer(MERGE, _deps() + [src, os.path.join(HERE, "host", "seed_merge.h")]):
+        return MERGE
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", src, "-o", MERGE], check=True)
+    return MERGE
+
+
 def build_oracle():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
     if os.path.isdir("/root/reference"):
@@ -64,6 +76,7 @@ def build_host():
 def build_all(verbose=False):
     build_cuda(verbose=verbose)
     build_emulator()
+    build_merge()
     build_oracle()
     build_host()
 

@@ -4,9 +4,9 @@
 //   processShiftXORswithSubstitutions    parse_substitute_shiftxor.cpp:391
 //   generateAnchoredShiftXORs            parse_anchored_shiftxor.cpp:20
 //   processShiftXORsAnchored             parse_anchored_shiftxor.cpp:538
-// Everything that consumes the candidates stays the reference's own host C++ and is linked from its unmodified
-// objects: the order-dependent merges addSeedToSeedPositions{Perfect,Substitutions,Anchored} (+ mergeAllLists), the
-// per-seed motif calling (processSeed, processSeedMotifWise), SSW and the CIGAR code. Build: compile this file in
+// The order-dependent merges addSeedToSeedPositions{Perfect,Substitutions,Anchored} (+ mergeAllLists) are restated in
+// seed_merge.cpp; the per-seed motif calling (processSeed, processSeedMotifWise), SSW and the CIGAR
+// code stay the reference's own host C++ and are linked from its unmodified objects. Build: compile this file in
 // place of fasta_utils.cpp and link libribbit_scan.so (ribbit_b200/host/Makefile).
 //
 // No scan happens on the CPU here: without a usable CUDA device the program stops with an error.
@@ -39,22 +39,12 @@
 #include "parse_seed.h"
 #include "parse_smallmotif_seed.h"
 #include "ribbit_scan.h"
+#include "seed_merge.h"
 #include "ssw_cpp.h"
 
 using namespace std;
 typedef vector<tuple<int, int, int, int>> SeedList;
 typedef boost::dynamic_bitset<> Bitset;
-
-// file-level functions of the reference that have external linkage but no header
-void addSeedToSeedPositionsPerfect(int seed_start, int seed_end, int motif_length, SeedList &seed_positions,
-                                   vector<Bitset> &motif_bsets, int bset_size);  // parse_perfect_shiftxor.cpp:47
-int addSeedToSeedPositionsSubstitutions(int seed_start, int seed_end, int motif_length, SeedList &seed_positions_perfect,
-                                        SeedList &seed_positions_substut, int *seedlen_cutoff, vector<Bitset> &motif_bsets,
-                                        int bset_size, int from_index, int seed_type);  // parse_substitute_shiftxor.cpp:18
-tuple<int, int> addSeedToSeedPositionsAnchored(int seed_start, int seed_end, int motif_length, SeedList &seed_positions_perfect,
-                                               SeedList &seed_positions_substut, SeedList &seed_positions_anchored,
-                                               int *seedlen_cutoffs, vector<Bitset> &motif_bsets, int bset_size,
-                                               tuple<int, int> from_indices, int seed_type);  // parse_anchored_shiftxor.cpp:113
 
 // the functions of fasta_utils.cpp that other reference files may reference
 void parseFai(string, int &, unordered_map<string, int> &) {}
@@ -263,7 +253,6 @@ bool forked_parts(int n_parts, int procs, ostream &out, Body body, Serve serve) 
     return true;
 }
 
-#ifndef RIBBIT_HOST_MOTIF
 // K7: rows chosen by the consensus-motif search (rb_motif_rows) for the top-level seeds of the current contig, computed in
 // one batch before the per-seed walk. key = seed_start | mlen << 32; value = {seed_sequence_length, row}.
 struct MotifRows {
@@ -271,11 +260,9 @@ struct MotifRows {
     long hits = 0, misses = 0;
     static uint64_t key(int start, int mlen) { return (uint64_t)(uint32_t)start | ((uint64_t)(uint32_t)mlen << 32); }
 } g_motif;
-#endif
 
 }  // namespace
 
-#ifndef RIBBIT_HOST_MOTIF
 // Replaces the reference's mostFrequentLongerMotif (parse_seed.cpp:153-256; ribbit_b200/host/Makefile renames that
 // definition, so processSeed's call at parse_seed.cpp:389 binds here): the row search runs on the GPU — batched ahead for
 // the top-level seeds, one rb_motif_rows call for the flank seeds processSeed recurses into (parse_seed.cpp:443-463) —
@@ -302,7 +289,6 @@ uint256_t mostFrequentLongerMotif(Bitset &left_bset, Bitset &right_bset, int &se
     }
     return unit;
 }
-#endif
 
 void processSequence(string &sequence_id, string &sequence, int window_length, int window_bitcount_threshold, int anchor_size,
                      int continuous_ones_threshold, ostream &out) {
@@ -329,107 +315,72 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     Bitset left_bset = to_bitset(hi.data(), sequence_length), right_bset = to_bitset(lo.data(), sequence_length),
            N_bset = to_bitset(nn.data(), sequence_length);
     // one-hot planes + per-base pointers (fasta_utils.cpp:83-115): only mostFrequentLongerMotif reads them, which runs on
-    // the GPU from the packed planes (K7) — they are built only when the host version is compiled in
+    // the GPU from the packed planes (K7): MATRIX stays empty
     vector<Bitset *> MATRIX;
-#ifdef RIBBIT_HOST_MOTIF
-    Bitset A(sequence_length, 0ull), T(sequence_length, 0ull), G(sequence_length, 0ull), C(sequence_length, 0ull);
-    MATRIX.reserve((size_t)sequence_length);
-    for (int i = 0; i < sequence_length; i++) {
-        const int bidx = (sequence_length - 1) - i;
-        switch (sequence[i]) {
-            case 'A': case 'a': MATRIX.push_back(&A); A[bidx] = 1; break;
-            case 'C': case 'c': MATRIX.push_back(&C); C[bidx] = 1; break;
-            case 'G': case 'g': MATRIX.push_back(&G); G[bidx] = 1; break;
-            case 'T': case 't': MATRIX.push_back(&T); T[bidx] = 1; break;
-            default: MATRIX.push_back(NULL); break;
-        }
-    }
-#endif
-    // fasta_utils.cpp:117-122: one match plane per shift, word-parallel already in the reference; the planes are
-    // independent of each other, so they are built on all host cores
+
+    // ---- the three order-dependent merges (addSeedToSeedPositions{Perfect,Substitutions,Anchored} + mergeAllLists),
+    // restated in seed_merge.cpp: they consume the streams as they are and take the few plane popcounts their tie-breakers
+    // need from the packed planes. Meanwhile worker threads build what only the per-seed stage reads: the anchored planes
+    // B_m as the reference's bitsets (fasta_utils.cpp:117-122, 143-161), from the anchor planes the GPU computed.
+    vector<uint32_t> anchors((size_t)nw * NSHIFTS + 1);
+    if (rb_get_anchor_planes(ctx, 0, MINIMUM_SHIFT, MAXIMUM_SHIFT, anchors.data()) != RB_OK) die("rb_get_anchor_planes", ctx);
     vector<Bitset> lshift_xor_bsets((size_t)NSHIFTS);
-    parallel_for(NSHIFTS, [&](int k) {
-        const int i = MINIMUM_SHIFT + k;
-        lshift_xor_bsets[(size_t)k] = ~(left_bset ^ (left_bset << (i))) & ~(right_bset ^ (right_bset << (i)));
-    });
-
-    clock.mark("code + match planes as bitsets");
-    SeedList seed_positions_perfect, seed_positions_substut, seed_positions_anchored;
-    const int bset_size = sequence_length;
-
-    // ---- perfect candidates -> the reference's merge (parse_perfect_shiftxor.cpp:182,202,219) ------------------
-    for (int64_t k = 0; k < st.n[RB_STREAM_PERFECT]; ++k) {
-        const rb_rec &r = st.rec[RB_STREAM_PERFECT][k];
-        addSeedToSeedPositionsPerfect(r.start, r.end, r.mlen, seed_positions_perfect, lshift_xor_bsets, bset_size);
-    }
-    cerr << "Total number of perfect seeds: " << seed_positions_perfect.size() << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
-
-    // ---- substitution candidates (parse_substitute_shiftxor.cpp:445…568) ---------------------------------------
-    {
-        vector<int> cut((size_t)NMOTIFS);
-        for (int midx = 0; midx < NMOTIFS; midx++) cut[(size_t)midx] = ((midx + MINIMUM_MLEN) > 30) ? (midx + MINIMUM_MLEN) / 3 : 10;  // :423
-        int from_index = 0;
-        for (int64_t k = 0; k < st.n[RB_STREAM_SUBST]; ++k) {
-            const rb_rec &r = st.rec[RB_STREAM_SUBST][k];
-            if (r.flags & RB_REC_PSEUDO) {
-                // calls the scan elided: only their cursor effect (…:34-42) matters, and only the largest end counts
-                if (r.end >= 0) from_index = addSeedToSeedPositionsSubstitutions(r.end, r.end, MINIMUM_MLEN, seed_positions_perfect, seed_positions_substut, cut.data(), lshift_xor_bsets, bset_size, from_index, RANK_S);
-                continue;
-            }
-            from_index = addSeedToSeedPositionsSubstitutions(r.start, r.end, r.mlen, seed_positions_perfect, seed_positions_substut, cut.data(), lshift_xor_bsets, bset_size, from_index, RANK_S);
-        }
-    }
-    {
-        int failed = 0;
-        for (auto &s : seed_positions_perfect) failed += get<3>(s) == -1;
-        for (auto &s : seed_positions_substut) failed += get<3>(s) == -1;
-        cerr << "Total number of seeds considering substitutions: " << seed_positions_perfect.size() + seed_positions_substut.size() - failed << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
-    }
-
-    // ---- anchored planes: anchors from the GPU, the 5-way OR as fasta_utils.cpp:146-160 -------------------------
-    {
-        vector<uint32_t> anchors((size_t)nw * NSHIFTS + 1);
-        if (rb_get_anchor_planes(ctx, 0, MINIMUM_SHIFT, MAXIMUM_SHIFT, anchors.data()) != RB_OK) die("rb_get_anchor_planes", ctx);
+    std::thread plane_builder([&] {
         vector<Bitset> lsxor_anchor_bsets((size_t)NSHIFTS);
-        parallel_for(NSHIFTS, [&](int s) { lsxor_anchor_bsets[(size_t)s] = to_bitset(anchors.data() + (size_t)s * nw, sequence_length); });
-        // B_m = X_m | A_i for the shifts i within two of m (from 1 when m <= 2), written over plane m in ascending m:
-        // planes m-2 and m-1 were already overwritten, but only their anchor planes are read (fasta_utils.cpp:146-160)
-        parallel_for(NMOTIFS, [&](int k) {  // plane m reads its own match plane and anchor planes only
+        parallel_for(NSHIFTS, [&](int k) {
+            const int i = MINIMUM_SHIFT + k;
+            lshift_xor_bsets[(size_t)k] = ~(left_bset ^ (left_bset << (i))) & ~(right_bset ^ (right_bset << (i)));
+            lsxor_anchor_bsets[(size_t)k] = to_bitset(anchors.data() + (size_t)k * nw, sequence_length);
+        });
+        // B_m = X_m | A_i for the shifts i within two of m (from 1 when m <= 2); plane m reads its own match plane and
+        // anchor planes only, so the planes can be overwritten in any order
+        parallel_for(NMOTIFS, [&](int k) {
             const int m = MINIMUM_MLEN + k;
             Bitset bm = lshift_xor_bsets[m - MINIMUM_SHIFT];
             for (int i = (m > 2) ? m - 2 : 1; i <= m + 2; ++i)
                 if (i != m) bm |= lsxor_anchor_bsets[i - MINIMUM_SHIFT];
             lshift_xor_bsets[m - MINIMUM_SHIFT] = bm;
         });
-    }
-    clock.mark("perfect + substitution merges, anchor planes");
-    cerr << "Generated anchored shift XORs!\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+    });
 
-    // ---- anchored candidates (parse_anchored_shiftxor.cpp:595…717) -----------------------------------------------
+    SeedList seed_positions_perfect, seed_positions_substut, seed_positions_anchored;
     {
-        vector<int> cut((size_t)NMOTIFS);
-        for (int midx = 0; midx < NMOTIFS; midx++) {  // :572-573
-            cut[(size_t)midx] = ((midx + MINIMUM_MLEN) > 6) ? (midx + MINIMUM_MLEN) : 10;
-            if (midx + MINIMUM_MLEN >= 10) cut[(size_t)midx] = 0.9 * (midx + MINIMUM_MLEN);
-        }
-        tuple<int, int> from_indices = {0, 0};
-        for (int64_t k = 0; k < st.n[RB_STREAM_ANCHORED]; ++k) {
-            const rb_rec &r = st.rec[RB_STREAM_ANCHORED][k];
-            if (r.flags & RB_REC_PSEUDO) {
-                if (r.end >= 0) from_indices = addSeedToSeedPositionsAnchored(r.end, r.end, MINIMUM_MLEN, seed_positions_perfect, seed_positions_substut, seed_positions_anchored, cut.data(), lshift_xor_bsets, bset_size, from_indices, RANK_A);
-                continue;
+        static_assert(sizeof(rb_rec) == sizeof(rbm::Cand), "rb_rec is read as {start, end, mlen | flags << 16, time}");
+        vector<rbm::Cand> cands[3];
+        const rbm::Cand *cp[3];
+        int64_t cn[3];
+        for (int s = 0; s < 3; ++s) {
+            cands[s].resize((size_t)st.n[s]);
+            for (int64_t k = 0; k < st.n[s]; ++k) {
+                const rb_rec &r = st.rec[s][k];
+                cands[s][(size_t)k] = rbm::Cand{r.start, r.end, r.mlen, r.flags};
             }
-            const tuple<int, int> ret = addSeedToSeedPositionsAnchored(r.start, r.end, r.mlen, seed_positions_perfect, seed_positions_substut, seed_positions_anchored, cut.data(), lshift_xor_bsets, bset_size, from_indices, RANK_A);
-            if (!(r.flags & RB_REC_NOCOMMIT)) from_indices = ret;  // tail-flush calls whose result the reference drops (:688-719)
+            cp[s] = cands[s].data(); cn[s] = st.n[s];
+        }
+        rbm::PackedPlaneCounts counts(hi.data(), lo.data(), nn.data(), sequence_length, MINIMUM_SHIFT, MAXIMUM_SHIFT);
+        rbm::SeedList lists[3];
+        rbm::run_merges(cp, cn, counts, MINIMUM_MLEN, MAXIMUM_MLEN, sequence_length, lists[0], lists[1], lists[2]);
+        SeedList *dst[3] = {&seed_positions_perfect, &seed_positions_substut, &seed_positions_anchored};
+        for (int s = 0; s < 3; ++s) {
+            dst[s]->reserve(lists[s].size());
+            for (const rbm::Seed &x : lists[s]) dst[s]->emplace_back(x.start, x.end, x.mlen, x.rank);
         }
     }
+    clock.mark("merges (restated, seed_merge.cpp)");
     {
+        // the reference's three progress lines (fasta_utils.cpp:134, 139, 170); the first two counts are taken after all
+        // passes here, so entries the anchored pass retired are already subtracted
         int failed = 0;
         for (auto &s : seed_positions_perfect) failed += get<3>(s) == -1;
         for (auto &s : seed_positions_substut) failed += get<3>(s) == -1;
+        cerr << "Total number of perfect seeds: " << seed_positions_perfect.size() << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+        cerr << "Total number of seeds considering substitutions: " << seed_positions_perfect.size() + seed_positions_substut.size() - failed << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
+        cerr << "Generated anchored shift XORs!\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
         for (auto &s : seed_positions_anchored) failed += get<3>(s) == -1;
         cerr << "Total number of seeds considering indels: " << seed_positions_perfect.size() + seed_positions_substut.size() + seed_positions_anchored.size() - failed << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
     }
+    plane_builder.join();
+    clock.mark("anchored planes as bitsets (overlapped with the merges)");
     if (const char *cp2 = getenv("RB_CP2_OUT")) {  // checkpoint CP2 for the parity tests: the three lists, same format as oracle/cp_hooks.h
         if (FILE *f = fopen(cp2, "ab")) {
             int32_t h[5] = {0, -1, sequence_length, 0, 0};
@@ -475,7 +426,6 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     vector<rb_seedinfo> info(todo.size());
     const bool use_filter = !getenv("RIBBIT_NO_SEED_FILTER");
     if (use_filter && !todo.empty() && rb_filter_seeds(ctx, todo.data(), (int64_t)todo.size(), info.data()) != RB_OK) die("rb_filter_seeds", ctx);
-#ifndef RIBBIT_HOST_MOTIF
     // K7: processSeed calls mostFrequentLongerMotif(seed_start, N-truncated seed length, mlen) for every seed with mlen > 10
     // that passes the gate (parse_seed.cpp:344-390) — all of them in one batch
     g_motif.rows.clear();
@@ -490,7 +440,6 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
         for (size_t k = 0; k < mseeds.size(); ++k)
             g_motif.rows.emplace(MotifRows::key(mseeds[k].start, mseeds[k].mlen), std::make_pair(mseeds[k].end - mseeds[k].start, mrows[k].row));
     }
-#endif
     vector<size_t> live;  // seeds that are handed to the per-seed functions, in processing order
     for (size_t k = 0; k < todo.size(); ++k)
         if (!(use_filter && info[k].longest_run < continuous_ones_threshold)) live.push_back(k);
@@ -512,7 +461,6 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
     const int procs = host_procs();
     long served = 0;
     bool in_workers = false;
-#ifndef RIBBIT_HOST_MOTIF
     if (procs > 1 && live.size() >= 4096) {
         // parts of roughly equal work (seed length + motif size as the weight), several per worker
         const int n_parts = (int)std::min<size_t>((size_t)procs * 8, live.size() / 256);
@@ -536,13 +484,10 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
         in_workers = done;
         if (!done) run_seeds(0, live.size(), out);
     } else
-#endif
         run_seeds(0, live.size(), out);
     clock.mark("per-seed stage");
-#ifndef RIBBIT_HOST_MOTIF
     if (getenv("RIBBIT_VERBOSE"))
         cerr << "K7 motif rows: " << g_motif.rows.size() << " in the batch, " << g_motif.misses + served << " single calls; per-seed stage on "
              << (in_workers ? procs : 1) << " process(es)\n";
-#endif
     cerr << "Total number of seeds that are processed for alignment: " << processed_seeds << "\t Time elapsed: " << difftime(time(0), START_TIME) << "secs\n";
 }
