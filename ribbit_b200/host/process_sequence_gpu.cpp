@@ -357,7 +357,7 @@ void processSequence(string &sequence_id, string &sequence, int window_length, i
             }
             cp[s] = cands[s].data(); cn[s] = st.n[s];
         }
-        rbm::PackedPlaneCounts counts(hi.data(), lo.data(), nn.data(), sequence_length, MINIMUM_SHIFT, MAXIMUM_SHIFT);
+        rbm::AnchorArrayCounts counts(hi.data(), lo.data(), nn.data(), sequence_length, MINIMUM_SHIFT, MAXIMUM_SHIFT, anchors.data());
         rbm::SeedList lists[3];
         rbm::run_merges(cp, cn, counts, MINIMUM_MLEN, MAXIMUM_MLEN, sequence_length, lists[0], lists[1], lists[2]);
         SeedList *dst[3] = {&seed_positions_perfect, &seed_positions_substut, &seed_positions_anchored};

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <deque>
 #include <map>
 
 #include "../csrc/scan_core.h"
@@ -112,6 +113,24 @@ struct Ref {
     int index;
 };
 
+// One scratch vector per recursion depth and thread, so that a call does not allocate (there are ~0.2 calls per base).
+struct Scratch {
+    std::deque<std::vector<Ref>> near, ps;  // a deque: growing it does not move the vectors the shallower calls use
+    int depth = 0;
+};
+thread_local Scratch g_scratch;
+struct ScratchUse {
+    std::vector<Ref>& near;
+    std::vector<Ref>& ps;
+    static std::vector<Ref>& at(std::deque<std::vector<Ref>>& pool, int d) {
+        if ((int)pool.size() <= d) pool.resize((size_t)d + 1);
+        pool[(size_t)d].clear();
+        return pool[(size_t)d];
+    }
+    ScratchUse() : near(at(g_scratch.near, g_scratch.depth)), ps(at(g_scratch.ps, g_scratch.depth)) { ++g_scratch.depth; }
+    ~ScratchUse() { --g_scratch.depth; }
+};
+
 // the seeds of the perfect and the substitution list that can touch a candidate starting at seed_start, interleaved by
 // descending end (ties: perfect first), retired ones left out; parse_substitute_shiftxor.cpp:47-113
 void candidates_ps(const SeedList& perfect, const SeedList& subst, int from_perfect, int seed_start, std::vector<Ref>& out) {
@@ -160,7 +179,8 @@ int add_subst(const MergeConfig& cfg, const PlaneCounts& planes, int seed_start,
     from_index = advance_cursor(perfect, from_index, seed_end);
     if (seed_end - seed_start < cfg.cut[mlen - cfg.min_mlen]) return from_index;  // :44
 
-    std::vector<Ref> near;
+    ScratchUse scratch;
+    std::vector<Ref>& near = scratch.near;
     candidates_ps(perfect, subst, from_index, seed_start, near);
 
     const int seed_length = seed_end - seed_start, seed_rlen = seed_length + mlen;
@@ -285,8 +305,7 @@ namespace {
 // from_subst); then that interleaving, walked from its END, against the anchored list from its end.
 // An empty substitution list counts as exhausted (the reference reads its first element and crashes).
 void candidates_psa(const SeedList& perfect, const SeedList& subst, const SeedList& anchored, int from_perfect, int from_subst,
-                    int seed_start, std::vector<Ref>& out) {
-    std::vector<Ref> ps;
+                    int seed_start, std::vector<Ref>& ps, std::vector<Ref>& out) {
     bool done_p = perfect.empty(), done_s = subst.empty();
     int ip = from_perfect, is = from_subst;
     while (!(done_p && done_s)) {
@@ -378,8 +397,9 @@ std::pair<int, int> add_anchored(const MergeConfig& cfg, const PlaneCounts& plan
     const std::pair<int, int> cursors(from_p, from_s);
     if (seed_end - seed_start < cfg.cut[mlen - cfg.min_mlen]) return cursors;  // :153
 
-    std::vector<Ref> near;
-    candidates_psa(perfect, subst, anchored, from_p, from_s, seed_start, near);
+    ScratchUse scratch;
+    std::vector<Ref>& near = scratch.near;
+    candidates_psa(perfect, subst, anchored, from_p, from_s, seed_start, scratch.ps, near);
 
     const int seed_length = seed_end - seed_start, seed_rlen = seed_length + mlen;
     // the recursive calls restart from the cursors this call was given, not from the advanced ones (:240, :261, ...)
@@ -644,6 +664,28 @@ int PackedPlaneCounts::anchored(int mlen, int a, int b) const {
         uint32_t v = p_->x(w, mlen);
         for (int i = (mlen > 2) ? mlen - 2 : 1; i <= mlen + 2; ++i)
             if (i != mlen && i >= p_->s_lo && i <= p_->s_hi) v |= p_->anchor(w, i);
+        return v;
+    });
+}
+
+// ---- plane counts with the anchor planes given (the binding has them anyway: the per-seed stage reads the anchored planes)
+struct AnchorArrayCounts::Impl {
+    PackedPlaneCounts::Impl* base;
+    const uint32_t* anchors;
+    long nw;
+};
+AnchorArrayCounts::AnchorArrayCounts(const uint32_t* hi, const uint32_t* lo, const uint32_t* nn, int contig_len, int min_shift, int max_shift,
+                                     const uint32_t* anchors)
+    : PackedPlaneCounts(hi, lo, nn, contig_len, min_shift, max_shift), q_(new Impl) {
+    q_->base = impl(); q_->anchors = anchors; q_->nw = ((long)contig_len + 31) / 32;
+}
+AnchorArrayCounts::~AnchorArrayCounts() { delete q_; }
+int AnchorArrayCounts::anchored(int mlen, int a, int b) const {
+    const PackedPlaneCounts::Impl* p = q_->base;
+    return p->count(a, b, [&](int w) {
+        uint32_t v = p->x(w, mlen);
+        for (int i = (mlen > 2) ? mlen - 2 : 1; i <= mlen + 2; ++i)
+            if (i != mlen && i >= p->s_lo && i <= p->s_hi) v |= q_->anchors[(size_t)(i - p->s_lo) * (size_t)q_->nw + (size_t)w];
         return v;
     });
 }

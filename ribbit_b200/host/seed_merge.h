@@ -67,10 +67,27 @@ public:
     ~PackedPlaneCounts();
     int match(int mlen, int a, int b) const override;
     int anchored(int mlen, int a, int b) const override;
+    struct Impl;
+
+protected:
+    Impl* impl() const { return p_; }
+
+private:
+    Impl* p_;
+};
+
+// The same with the anchor planes A_s given as rb_get_anchor_planes returns them (anchors[(s - min_shift) * ceil(L/32) + w]):
+// B_m words are then plain ORs. The drop-in binding fetches these planes anyway for the per-seed stage.
+class AnchorArrayCounts : public PackedPlaneCounts {
+public:
+    AnchorArrayCounts(const uint32_t* hi, const uint32_t* lo, const uint32_t* nn, int contig_len, int min_shift, int max_shift,
+                      const uint32_t* anchors);
+    ~AnchorArrayCounts();
+    int anchored(int mlen, int a, int b) const override;
 
 private:
     struct Impl;
-    Impl* p_;
+    Impl* q_;
 };
 
 }  // namespace rbm
