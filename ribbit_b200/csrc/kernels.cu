@@ -317,7 +317,9 @@ __device__ __forceinline__ void tight_step(TightLoop& q, const TightState& in, T
     q.off = off;
     ++q.mp; ++q.cp;
     tight_rotate(t, xn);
-    q.vprev = q.vcur; q.vcur = o.w;
+    // (whole-warp items: the word is the same in every lane, which the compiler cannot see through the load; the broadcast
+    // makes the loop condition provably uniform, so the warp-level operations of the next step need no convergence guards)
+    q.vprev = q.vcur; q.vcur = WHOLE ? __shfl_sync(FULL, o.w, 0) : o.w;
     ++q.w;
 }
 
@@ -328,12 +330,17 @@ __device__ __noinline__ void tight_run(TightIO* io) {
     q.cw = io->cw; q.raw = io->raw;
     q.off = io->off; q.cap_end = io->cap_end;
     q.w = io->w; q.wend = io->wend; q.L = io->L;
+    if (BW == 32) {  // uniform by construction; say so (see tight_step)
+        q.w = __shfl_sync(0xFFFFFFFFu, q.w, 0); q.wend = __shfl_sync(0xFFFFFFFFu, q.wend, 0); q.L = __shfl_sync(0xFFFFFFFFu, q.L, 0);
+        q.off = __shfl_sync(0xFFFFFFFFu, q.off, 0); q.cap_end = __shfl_sync(0xFFFFFFFFu, q.cap_end, 0);
+    }
     q.on = BW == 32 ? true : io->on != 0;
     q.po = reinterpret_cast<const uint4*>(q.cw + (q.w + 1));
     q.pb = reinterpret_cast<const uint2*>(q.cw + (q.w + 1 + (q.c.s >> 5) + 1));
     q.mp = io->meta + q.w;
     q.cp = io->bcnt + q.w;
     q.vprev = q.on ? v_eff(q.cw, q.w - 1) : 0xFFFFFFFFu; q.vcur = q.on ? q.cw[q.w].v : 0xFFFFFFFFu;
+    if (BW == 32) { q.vprev = __shfl_sync(0xFFFFFFFFu, q.vprev, 0); q.vcur = __shfl_sync(0xFFFFFFFFu, q.vcur, 0); }
     // flags of the two words in front: unknown, so the first steps take the exact anchors; t.lenL is the general path's
     // carried run length
     q.flags = TF_SUSC | TF_SUSP | TF_PREV_RARE;
