@@ -184,6 +184,13 @@ __device__ __noinline__ void tight_exact(ExactIO* e, const PlaneWord* cw, int w,
     if (e->cand) e->cand = kept_exact_perfect(cw, w, s, cut_perfect(s), e->xc, e->sx, e->cand);
 }
 
+template <typename T>
+__device__ __forceinline__ T* uniform_ptr(T* p) {
+    const unsigned long long v = (unsigned long long)p;
+    const unsigned lo = __shfl_sync(0xFFFFFFFFu, (unsigned)v, 0), hi = __shfl_sync(0xFFFFFFFFu, (unsigned)(v >> 32), 0);
+    return (T*)(((unsigned long long)hi << 32) | lo);
+}
+
 // everything the loop carries besides the per-word lane state
 struct TightLoop {
     TightCfg c;
@@ -330,15 +337,18 @@ __device__ __noinline__ void tight_run(TightIO* io) {
     q.cw = io->cw; q.raw = io->raw;
     q.off = io->off; q.cap_end = io->cap_end;
     q.w = io->w; q.wend = io->wend; q.L = io->L;
-    if (BW == 32) {  // uniform by construction; say so (see tight_step)
+    Meta* meta = io->meta;
+    uint32_t* bcnt = io->bcnt;
+    if (BW == 32) {  // uniform by construction; say so (see tight_step): the values can then live in uniform registers
         q.w = __shfl_sync(0xFFFFFFFFu, q.w, 0); q.wend = __shfl_sync(0xFFFFFFFFu, q.wend, 0); q.L = __shfl_sync(0xFFFFFFFFu, q.L, 0);
         q.off = __shfl_sync(0xFFFFFFFFu, q.off, 0); q.cap_end = __shfl_sync(0xFFFFFFFFu, q.cap_end, 0);
+        q.cw = uniform_ptr(q.cw); q.raw = uniform_ptr(q.raw); meta = uniform_ptr(meta); bcnt = uniform_ptr(bcnt);
     }
     q.on = BW == 32 ? true : io->on != 0;
     q.po = reinterpret_cast<const uint4*>(q.cw + (q.w + 1));
     q.pb = reinterpret_cast<const uint2*>(q.cw + (q.w + 1 + (q.c.s >> 5) + 1));
-    q.mp = io->meta + q.w;
-    q.cp = io->bcnt + q.w;
+    q.mp = meta + q.w;
+    q.cp = bcnt + q.w;
     q.vprev = q.on ? v_eff(q.cw, q.w - 1) : 0xFFFFFFFFu; q.vcur = q.on ? q.cw[q.w].v : 0xFFFFFFFFu;
     if (BW == 32) { q.vprev = __shfl_sync(0xFFFFFFFFu, q.vprev, 0); q.vcur = __shfl_sync(0xFFFFFFFFu, q.vcur, 0); }
     // flags of the two words in front: unknown, so the first steps take the exact anchors; t.lenL is the general path's
