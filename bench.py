@@ -449,11 +449,18 @@ def run_gpu(args):
     # (rb_load_contigs), runs the kernels and copies its three streams back (rb_fetch_compact). Contigs go through
     # ribbit_b200.pipeline.ScanPipeline one by one: three contexts on the GPU, so the copies of one contig overlap the
     # kernels of the next. All results of all K steps are complete inside the timed region.
-    units = [(c, None) for c in whole] + [(c, (a, b)) for c, a, b in ranges]
+    # Whole contigs that lie next to each other in the host buffer go in batches of about --e2e-batch-mbp (the kernels run
+    # at their large-batch rate); the smallest batch goes first (short pipeline fill), then the largest ones.
+    units = [(g, None) for g in pipeline.group_contigs(sorted(whole), lengths, args.e2e_batch_mbp * 1_000_000)]
+    units.sort(key=lambda u: -sum(lengths[c] for c in u[0]))
+    if len(units) > 2:
+        units.insert(0, units.pop())
+    units += [([c], (a, b)) for c, a, b in ranges]
     pipe = pipeline.ScanPipeline(M_LO, M_HI, device=local, depth=args.depth, compact=True)
 
     def submit_all():
-        return [pipe.submit_flat(host_np[offs[c]:offs[c] + lengths[c] + 1], [lengths[c]], rng) for c, rng in units]
+        return [pipe.submit_flat(host_np[offs[g[0]]:offs[g[-1]] + lengths[g[-1]] + 1], [lengths[c] for c in g], rng,
+                                 offsets=[offs[c] - offs[g[0]] for c in g]) for g, rng in units]
 
     for f in submit_all():
         f.result()
@@ -474,8 +481,8 @@ def run_gpu(args):
     if e2e_counts != counts:
         sys.stderr.write("bench.py: end-to-end streams differ from the device-resident ones: %s vs %s\n" % (e2e_counts, counts))
         os._exit(3)
-    h2d = int(allsum(sum(lengths[c] for c, _ in units)))
-    d2h = int(allsum(sum(e2e_counts) * 8 + len(units) * 3 * 2 * 8))
+    h2d = int(allsum(sum(lengths[c] for g, _ in units for c in g)))
+    d2h = int(allsum(sum(e2e_counts) * 8 + sum(len(g) + 1 for g, _ in units) * 3 * 8))
     pipe.close()
 
     # ---- rank 0 only, outside the timed regions: the other BASELINE.json shapes (device-resident, few steps), the rows
@@ -591,7 +598,7 @@ def run_gpu(args):
                        "input_generation_s": gen_s, "also": also},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "per step and contig: rb_load_contigs (pinned host ASCII -> HBM) + rb_scan_device (kernels) + rb_fetch_compact (D2H of the three streams as 8-byte records); contigs pipelined over %d contexts per GPU (ribbit_b200.pipeline)" % args.depth,
+                    "what": "per step and batch: rb_load_contigs (pinned host ASCII -> HBM) + rb_scan_device (kernels) + rb_fetch_compact (D2H of the three streams as 8-byte records); batches of about %d Mbp pipelined over %d contexts per GPU, one batch's kernels at a time (ribbit_b200.pipeline)" % (args.e2e_batch_mbp, args.depth),
                     "pcie_gbs_per_direction": pcie_each,
                     "pcie_ceiling_gbps": world * min(pcie_each * 1e9 / (h2d / genome), pcie_each * 1e9 / (d2h / genome)) / 1e9 if h2d and d2h else None,
                     "pcie_note": "plain cudaMemcpyAsync of 1 GiB pinned buffers, H2D and D2H at the same time, all ranks at once; ceiling = that rate over the bytes per base each direction moves"},
@@ -622,6 +629,7 @@ def main():
     ap.add_argument("--no-gate", action="store_true", help="skip the parity gate (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip C2 / C5 / K0 / K7 / CPU-baseline legs (profiling runs)")
     ap.add_argument("--depth", type=int, default=4, help="scan contexts per GPU in the end-to-end pipeline")
+    ap.add_argument("--e2e-batch-mbp", type=int, default=400, help="bases per batch of the end-to-end pipeline (whole contigs)")
     ap.add_argument("--c5-contigs", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="bases per CPU-baseline process")
     ap.add_argument("--ref-sample", type=int, default=500_000, help="bases per process and step for --impl reference")

@@ -205,6 +205,37 @@ def test_pipeline_two_contexts_gives_same_streams(built):
     pipe.close()
 
 
+def test_pipeline_grouped_batches_with_offsets(built):
+    """The end-to-end path of bench.py: contigs at offsets of one host buffer, grouped into batches (group_contigs),
+    three contexts, compact fetch; every contig equals the oracle."""
+    from ribbit_b200 import pipeline
+    rng = np.random.default_rng(22)
+    seqs = [synth.fuzz_contig(rng, int(L), 0.002) for L in (30000, 12000, 0, 9000, 25000, 700, 18000)]
+    lengths = [len(s) for s in seqs]
+    offs, total = [], 0
+    for s in seqs:
+        offs.append(total); total += len(s) + 1
+    host = np.zeros(total + 64, dtype=np.uint8)
+    for o, s in zip(offs, seqs):
+        host[o:o + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    groups = pipeline.group_contigs(range(len(seqs)), lengths, 40000)
+    assert [c for g in groups for c in g] == list(range(len(seqs))) and len(groups) >= 3
+    pipe = pipeline.ScanPipeline(2, 100, depth=3, copy=True, compact=True, trace=True)
+    futs = [pipe.submit_flat(host[offs[g[0]]:offs[g[-1]] + lengths[g[-1]] + 1], [lengths[c] for c in g],
+                             offsets=[offs[c] - offs[g[0]] for c in g]) for g in groups]
+    for g, f in zip(groups, futs):
+        comp = f.result()
+        for k, c in enumerate(g):
+            exp = sm.expected_streams(seqs[c], ou.scan_events(seqs[c], 2, 100))
+            for st in range(3):
+                r8, off8, lg = comp[st]
+                rows = scan.expand_compact(r8, lg)[off8[k]:off8[k + 1]]
+                e = exp[st + 1][:, :4]  # (start, end, mlen, flags); the compact records carry no emission time
+                assert rows.shape == e.shape and (rows == e).all(), "contig %d stream %d" % (c, st)
+    assert len(pipe.trace) == len(groups)
+    pipe.close()
+
+
 def test_c5_shape_many_short_contigs(built):
     """BASELINE.json configs[4] shape (1 kb contigs, -m 1 -M 6), scaled to 20 000 contigs in one batch: a sample of contigs
     against the oracle (the reference itself segfaults on this shape after logging CP1), the rest through

@@ -134,3 +134,14 @@ def test_contig_split_two_ranks_gloo():
     whole = sm.expected_streams(seq, ou.scan_events(seq, 2, 30))
     for s in (1, 2, 3):
         assert np.array_equal(np.array(got[s], dtype=np.int64).reshape(-1, 5), whole[s])
+
+
+def test_group_contigs_batches_adjacent_contigs():
+    from ribbit_b200 import pipeline
+    lengths = [50, 40, 30, 100, 5, 5, 5, 70]
+    g = pipeline.group_contigs(range(8), lengths, 80)
+    assert g == [[0], [1, 2], [3], [4, 5, 6], [7]]
+    assert sum(len(x) for x in g) == 8
+    # contigs that are not neighbours in the host buffer never share a batch
+    assert pipeline.group_contigs([0, 2, 3, 6], lengths, 1000) == [[0], [2, 3], [6]]
+    assert pipeline.group_contigs([], lengths, 10) == []

@@ -10,7 +10,7 @@ flat = b"".join(synth.contigs_c5(n=n, length=1000, seed=5))
 h = torch.empty(len(flat) + 64, dtype=torch.uint8, pin_memory=True)
 h.numpy()[:len(flat)] = np.frombuffer(flat, dtype=np.uint8)
 d = h.cuda()
-sc = scan.Scanner(1, 6)
+sc = scan.Scanner(1, 6, debug=int(os.environ.get("RB_DEBUG", "0")))
 sc.load_device(d.data_ptr(), [1000] * n, keepalive=d)
 for _ in range(steps):
     sc.scan_device()
