@@ -456,15 +456,20 @@ def run_gpu(args):
     if len(units) > 2:
         units.insert(0, units.pop())
     units += [([c], (a, b)) for c, a, b in ranges]
-    pipe = pipeline.ScanPipeline(M_LO, M_HI, device=local, depth=args.depth, compact=True)
+    trace = os.environ.get("RB_E2E_TRACE") == "1"  # diagnostic: rank 0 prints the pipeline timeline of the timed steps
+    pipe = pipeline.ScanPipeline(M_LO, M_HI, device=local, depth=args.depth, compact=True, trace=trace)
 
     def submit_all():
+        pipe.n = 0  # every step maps batch i to context i % depth: the contexts' buffers reach their final size in the warm-up
         return [pipe.submit_flat(host_np[offs[g[0]]:offs[g[-1]] + lengths[g[-1]] + 1], [lengths[c] for c in g], rng,
                                  offsets=[offs[c] - offs[g[0]] for c in g]) for g, rng in units]
 
-    for f in submit_all():
-        f.result()
+    for _ in range(max(1, args.warmup)):
+        for f in submit_all():
+            f.result()
     barrier()
+    if trace:
+        pipe.trace.clear()
     t0 = time.perf_counter()
     e2e_counts = [0, 0, 0]
     futs = []
@@ -478,6 +483,10 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_s = allmax(time.perf_counter() - t0)
     e2e_value = genome * args.steps / e2e_s / 1e9
+    if trace:
+        for k, nb, a, b_, c_, d_, e_ in sorted(pipe.trace, key=lambda x: x[2]):
+            sys.stderr.write("rank %d " % rank + "ctx %d %9d bases: load %7.1f..%7.1f scan %7.1f..%7.1f fetch ..%7.1f ms\n" % (
+                k, nb, (a - t0) * 1e3, (b_ - t0) * 1e3, (c_ - t0) * 1e3, (d_ - t0) * 1e3, (e_ - t0) * 1e3))
     if e2e_counts != counts:
         sys.stderr.write("bench.py: end-to-end streams differ from the device-resident ones: %s vs %s\n" % (e2e_counts, counts))
         os._exit(3)
