@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
         if (__any_sync(0xFFFFFFFFu, want) && __all_sync(0xFFFFFFFFu, want || !active)) {
             TightIO io;
             tight_enter(cfg, st, io.t);
-            io.c = make_tight_cfg(cfg);
+            io.c = make_tight_cfg(cfg, tier == TIER_LARGE);
             io.cw = cw; io.meta = meta; io.bcnt = bcnt; io.raw = b.raw; io.off = off; io.cap_end = off0 + (uint32_t)sk.cap;
             io.w = w; io.wend = wend; io.L = L; io.on = want ? 1 : 0;
             io.lt = (1u << lane) - 1u;
@@ -631,6 +631,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             else tight_run<BW, TIER_LARGE>(&io);
             if (want) {
                 tight_leave(io.t, st);
+                if (tier == TIER_LARGE && io.w != w && cfg.motif) smear_from_last(cfg, st, io.w);  // (scan_tight.h tight_events_A)
                 if (io.w != w && cfg.s) st.xc.idx = io.w + (cfg.s >> 5) + 1;  // the cached plane word: the last b operand
                 w = io.w;
                 off = io.off;

@@ -448,6 +448,37 @@ RB_HD uint32_t smear_step(const LaneCfg& cfg, LaneState& st, uint32_t S, uint32_
     return v;
 }
 
+// The same filter without the smear network, for lanes whose cutoff is at least 32 (exact for every such cutoff): the E
+// bit at position p0 + i belongs to the component that started at the latest S bit in front of it. An S bit below i in the
+// same word is less than 32 positions back: below the cutoff. Otherwise the start is lastS and the component is kept iff
+// p0 + i - lastS - 1 >= cut, i.e. i >= lastS + cut + 1 - p0 (merge_core.h entry_interval computes the same interval).
+// cut1 = cut + 1.
+RB_HD uint32_t keep_by_last(uint32_t E, uint32_t S, int lastS, int cut1, int p0) {
+    const uint32_t below = S ^ (S - 1u);  // bits up to and including the lowest S bit of the word (all bits when it has none):
+                                          // an S bit AT i starts the next component, it is not in front of i
+    int thr = lastS + cut1 - p0;
+    thr = thr < 0 ? 0 : thr;
+#ifdef __CUDA_ARCH__
+    const uint32_t far = __funnelshift_lc(0u, 0xFFFFFFFFu, thr);  // bits thr..31; none for thr >= 32 (the shift clamps)
+#else
+    const uint32_t far = thr >= 32 ? 0u : (0xFFFFFFFFu << thr);
+#endif
+    return E & below & far;
+}
+// The smear state a lane needs when it goes back to smear_step after words filtered by keep_by_last (w = the next word):
+// what any later E bit asks is whether the LATEST S bit lies within n positions, so a history that holds just that one
+// bit gives the same answers as the true one. Replays the four words in front of w (the network looks back 96 positions).
+RB_HD void smear_from_last(const LaneCfg& cfg, LaneState& st, int w) {
+    for (int i = 0; i < 7; ++i) st.sm[i] = 0u;
+    const int lastS = st.ea.lastS;
+    uint32_t Sprev = 0u;
+    for (int k = 4; k >= 1; --k) {
+        const uint32_t S = (lastS >= 0 && (lastS >> 5) == w - k) ? (1u << (lastS & 31)) : 0u;
+        smear_step(cfg, st, S, Sprev);
+        Sprev = S;
+    }
+}
+
 // ---- fast word -----------------------------------------------------------------------------------------------------
 // A fast word hands its candidates over as MASK ENTRIES (Sink::entry): per stream the E bits (perfect stream: the run ends)
 // that survived the bit-parallel prefilters, the S mask (run starts) of the word and the position of the latest S bit in

@@ -25,7 +25,7 @@ struct TightCfg {
     uint32_t amask;      // ~0 for lanes that own a shift, 0 for idle lanes (their anchors must read as 0)
     uint32_t mmask;      // ~0 for motif lanes
     int d0, d1, d2, d3;  // smear shifts of the anchored keep filter, levels 0-3 (SMALL items; else 1, 2, 4, 8)
-    int d4, d5, d6;      //   levels 4-6
+    int d4, d5, d6;      //   levels 4-6 (LARGE items: d4 = anchored cutoff + 1, the others unused: keep_by_last)
     int e0, e1, e2, e3, e4;  // doubling shifts of "K2 ones in a row" (SMALL items)
 };
 
@@ -40,7 +40,7 @@ struct TightState {
     uint32_t p8, p16;      // MID / LARGE: previous word of "8 / 16 ones of X_s in a row end here" (perfect-run prefilter)
 };
 
-RB_HD TightCfg make_tight_cfg(const LaneCfg& c) {
+RB_HD TightCfg make_tight_cfg(const LaneCfg& c, bool large = false) {  // large: the item runs tight_run<.., TIER_LARGE>
     TightCfg t;
     t.s = c.s; t.sh = c.s & 31; t.K2 = 2 * c.s;
     t.exactA = c.cutA <= SMEAR_MAX;
@@ -48,6 +48,7 @@ RB_HD TightCfg make_tight_cfg(const LaneCfg& c) {
     t.mmask = c.motif ? 0xFFFFFFFFu : 0u;
     t.d0 = (int)(c.dA & 63u); t.d1 = (int)((c.dA >> 6) & 63u); t.d2 = (int)((c.dA >> 12) & 63u); t.d3 = (int)((c.dA >> 18) & 63u);
     t.d4 = (int)((c.dA >> 24) & 63u); t.d5 = (int)(c.dA2 & 63u); t.d6 = (int)((c.dA2 >> 6) & 63u);
+    if (large) { t.d4 = c.cutA + 1; t.exactA = 1; }
     // five doubling steps reach min(K2, 32) ones in a row
     int k = 1, e[5];
     for (int i = 0; i < 5; ++i) {
@@ -196,6 +197,14 @@ template <int TIER>
 RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t passA, TightOut& o) {
     uint32_t sA, eA, sAp;
     ev_step(passA, t.ea, sA, eA, sAp);
+    if (TIER == TIER_LARGE) {
+        // every motif size of a LARGE item is at least 50: anchored cutoffs of 45 and more, decided from the position of
+        // the latest S bit (exact for every cutoff; t.sm is not maintained: smear_from_last when the loop is left)
+        o.x = keep_by_last(eA, sA, t.ea.lastS, c.d4, p0);
+        o.e = eA; o.s = sA; o.last = t.ea.lastS;
+        t.ea.lastS = sA ? p0 + 31 - clz32(sA) : t.ea.lastS;
+        return;
+    }
     uint32_t v = fsl(sAp, sA, 1);
 #define RB_TSMEAR(i, d)                                  \
     {                                                    \
@@ -205,7 +214,7 @@ RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t pas
     }
     // every motif size of a MID / LARGE item has a cutoff of at least 16: the first four levels are plain doublings
     if (TIER == TIER_SMALL) { RB_TSMEAR(0, c.d0) RB_TSMEAR(1, c.d1) RB_TSMEAR(2, c.d2) RB_TSMEAR(3, c.d3) }
-    else { RB_TSMEAR(0, 1) RB_TSMEAR(1, 2) RB_TSMEAR(2, 4) RB_TSMEAR(3, 8) }
+    else { RB_TSMEAR(0, 1) RB_TSMEAR(1, 2) RB_TSMEAR(2, 4) RB_TSMEAR(3, 8) }  // (MID: every cutoff is at least 16)
     RB_TSMEAR(4, c.d4) RB_TSMEAR(5, c.d5) RB_TSMEAR(6, c.d6)
 #undef RB_TSMEAR
     o.x = eA & ~v; o.e = eA; o.s = sA; o.last = t.ea.lastS;

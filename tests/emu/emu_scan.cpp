@@ -75,7 +75,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
     const int bw = lay.bw;
     TightState ts[32];
     TightCfg tc[32];
-    for (int j = 0; j < bw; ++j) { tight_enter(cfg[j], st[j], ts[j]); tc[j] = make_tight_cfg(cfg[j]); }
+    for (int j = 0; j < bw; ++j) { tight_enter(cfg[j], st[j], ts[j]); tc[j] = make_tight_cfg(cfg[j], TIER == TIER_LARGE); }
     uint32_t vprev = v_eff(cw, w - 1), vcur = cw[w].v;
     bool susp = true, susc = true, prev_rare = true;
     int zc = 0;
@@ -136,6 +136,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
     for (int j = 0; j < bw; ++j) {
         if (TIER != TIER_SMALL && tc[j].s && !prev_rare) ts[j].lenL = tight_lenL_lookup(tc[j], ts[j], cw, w);
         tight_leave(ts[j], st[j]);
+        if (TIER == TIER_LARGE && w != w_in && cfg[j].motif) smear_from_last(cfg[j], st[j], w);
         if (w != w_in && cfg[j].s) st[j].xc.idx = w + (cfg[j].s >> 5) + 1;
     }
     return steps;
