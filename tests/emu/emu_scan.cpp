@@ -146,6 +146,42 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
 
 extern "C" {
 
+// Property check of the large-shift keep filter (scan_core.h keep_by_last, smear_from_last) on random event words:
+//  (1) keep_by_last == kept_exact for every cutoff >= 32;
+//  (2) a lane that goes back to the smear network with the state smear_from_last builds gets the answers the network
+//      gives when it ran all along (cutoffs <= SMEAR_MAX).
+// Returns the number of disagreements.
+int emu_keep_filter_check(uint64_t seed, int rounds) {
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    auto sparse = [&](int k) { uint32_t v = 0xFFFFFFFFu; for (int i = 0; i < k; ++i) v &= (uint32_t)rnd(); return v; };
+    int bad = 0;
+    for (int r = 0; r < rounds; ++r) {
+        const int m = 36 + (int)(rnd() % 965);  // cut_anch(m) >= 32
+        const LaneCfg cfg = make_lane_cfg(m, 2, 1000, 1, 1002, 2, 1000);
+        const int cut = cfg.cutA;
+        LaneState full, rebuilt;
+        for (int i = 0; i < 7; ++i) full.sm[i] = 0u;
+        int lastS = -1;
+        uint32_t Sprev = 0u;
+        const int nwords = 40, sw = 8 + (int)(rnd() % 24);  // the second lane switches to the network at word sw
+        for (int w = 0; w < nwords; ++w) {
+            // (an E bit always has an S bit in front of it: the first word starts a component and ends none)
+            const uint32_t S = w ? sparse(3 + (int)(rnd() % 3)) : 1u, E = w ? sparse(2 + (int)(rnd() % 3)) : 0u;
+            const int p0 = 32 * w;
+            const uint32_t exact = kept_exact(cut, p0, E, S, lastS);
+            if (keep_by_last(E, S, lastS, cut + 1, p0) != exact) ++bad;
+            const uint32_t vfull = E & ~smear_step(cfg, full, S, Sprev);
+            if (cut <= SMEAR_MAX && vfull != exact) ++bad;
+            if (w == sw) { rebuilt.ea.lastS = lastS; smear_from_last(cfg, rebuilt, w); }
+            if (w >= sw && cut <= SMEAR_MAX && (E & ~smear_step(cfg, rebuilt, S, Sprev)) != exact) ++bad;
+            if (S) lastS = p0 + 31 - clz32(S);
+            Sprev = S;
+        }
+    }
+    return bad;
+}
+
 // Returns the three ordered streams concatenated per stream: out[stream] malloc'ed arrays of Rec, counts in n[3].
 // restarts (optional) receives the number of warm-up restarts.
 int emu_scan(const char* seq, int64_t L, int m_lo, int m_hi, int chunk_words, int warm0, Rec** out, int64_t* n,

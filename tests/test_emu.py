@@ -131,3 +131,14 @@ def test_emulator_large_motif_sizes(mlo, mhi):
         for cw in (1 << 30, 7):
             got, _ = emu_util.emu_streams(seq, mlo, mhi, cw)
             _same(got, exp)
+
+
+def test_keep_filter_of_the_large_shift_loop():
+    """scan_core.h keep_by_last (anchored cutoff from the position of the latest S bit) equals the bit-by-bit check for every
+    cutoff >= 32, and smear_from_last hands a lane back to the smear network with a state that gives the same answers."""
+    import ctypes
+    L = emu_util.lib()
+    L.emu_keep_filter_check.restype = ctypes.c_int
+    L.emu_keep_filter_check.argtypes = [ctypes.c_uint64, ctypes.c_int]
+    for seed in (1, 2, 3):
+        assert L.emu_keep_filter_check(seed, 4000) == 0
