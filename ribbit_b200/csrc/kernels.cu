@@ -278,7 +278,8 @@ __device__ __forceinline__ void tight_step(TightLoop& q, const TightState& in, T
     }
     // survivors of the prefilters that are not decided yet: exact check, bit by bit (rare)
     // (substitution stream: the prefilter is the cutoff itself while that is 10, i.e. for motif sizes up to 30)
-    const uint32_t needA = c.exactA ? 0u : oa.x, needS = c.s > 30 ? os.x : 0u;
+    // (LARGE items: the anchored filter is exact for every cutoff, and every motif size is above 30)
+    const uint32_t needA = (TIER == TIER_LARGE || c.exactA) ? 0u : oa.x, needS = (TIER == TIER_LARGE || c.s > 30) ? os.x : 0u;
     if (__any_sync(FULL, (needA | needS | cand) != 0u)) {
         ExactIO ex;
         ex.xA = oa.x; ex.sA = oa.s; ex.lastA = oa.last; ex.xS = os.x; ex.sS = os.s; ex.lastS = os.last;

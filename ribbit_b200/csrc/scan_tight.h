@@ -179,7 +179,12 @@ RB_HD void tight_windows(const TightCfg& c, TightState& t, uint32_t an, uint32_t
     const uint32_t o2p = t.cs.o2;
     passS = ~fail_ge2(x, l1, t.cs, cand) & c.mmask;
     passA = ~fail_ge3(x | an, t.ca) & c.mmask;
-    if (TIER != TIER_SMALL) {
+    if (TIER == TIER_LARGE) {
+        // every perfect cutoff of a LARGE item is at least 50 (parse_perfect_shiftxor.cpp:193): a run that long which ends
+        // inside this word started in an earlier one, so its end is the lowest zero bit of the word, and it covers at
+        // least the top 18 bits of the previous word (t.p8 / t.p16 are not maintained)
+        cand = (t.xp >= 0xFFFF0000u) ? (~x & (x + 1u)) : 0u;
+    } else if (TIER != TIER_SMALL) {
         // every perfect cutoff of these items is at least 18 (parse_perfect_shiftxor.cpp:193): only run ends that follow 16
         // ones can be candidates, which leaves almost nothing for the exact check
         const uint32_t o8 = ~(t.cs.o2 | fsl(o2p, t.cs.o2, 4));   // X_s[t-7..t] all ones
