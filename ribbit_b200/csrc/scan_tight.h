@@ -21,7 +21,7 @@ namespace rb {
 struct TightCfg {
     int s, sh;           // shift, s & 31
     int K2;              // 2 s (anchor run-length bound)
-    int exactA;          // the bit-parallel anchored keep filter is exact for this lane (cutA <= SMEAR_MAX)
+    int exactA;          // the bit-parallel anchored keep filter is exact for this lane (cutA <= SMEAR_MAX; LARGE items: always)
     uint32_t amask;      // ~0 for lanes that own a shift, 0 for idle lanes (their anchors must read as 0)
     uint32_t mmask;      // ~0 for motif lanes
     int d0, d1, d2, d3;  // smear shifts of the anchored keep filter, levels 0-3 (SMALL items; else 1, 2, 4, 8)
@@ -37,7 +37,7 @@ struct TightState {
     WinCarryA ca;
     EvCarry es, ea;
     uint32_t sm[7];
-    uint32_t p8, p16;      // MID / LARGE: previous word of "8 / 16 ones of X_s in a row end here" (perfect-run prefilter)
+    uint32_t p8, p16;      // MID: previous word of "8 / 16 ones of X_s in a row end here" (perfect-run prefilter)
 };
 
 RB_HD TightCfg make_tight_cfg(const LaneCfg& c, bool large = false) {  // large: the item runs tight_run<.., TIER_LARGE>
