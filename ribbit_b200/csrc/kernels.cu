@@ -278,8 +278,8 @@ __device__ __forceinline__ void tight_step(TightLoop& q, const TightState& in, T
     }
     // survivors of the prefilters that are not decided yet: exact check, bit by bit (rare)
     // (substitution stream: the prefilter is the cutoff itself while that is 10, i.e. for motif sizes up to 30)
-    // (LARGE items: the anchored filter is exact for every cutoff, and every motif size is above 30)
-    const uint32_t needA = (TIER == TIER_LARGE || c.exactA) ? 0u : oa.x, needS = (TIER == TIER_LARGE || c.s > 30) ? os.x : 0u;
+    // (the anchored filter is exact for every cutoff; LARGE items: every motif size is above 30)
+    const uint32_t needA = 0u, needS = (TIER == TIER_LARGE || c.s > 30) ? os.x : 0u;
     if (__any_sync(FULL, (needA | needS | cand) != 0u)) {
         ExactIO ex;
         ex.xA = oa.x; ex.sA = oa.s; ex.lastA = oa.last; ex.xS = os.x; ex.sS = os.s; ex.lastS = os.last;
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, RB_SCAN_BLOCKS_PER_SM) scan_k
             else tight_run<BW, TIER_LARGE>(&io);
             if (want) {
                 tight_leave(io.t, st);
-                if (tier == TIER_LARGE && io.w != w && cfg.motif) smear_from_last(cfg, st, io.w);  // (scan_tight.h tight_events_A)
+                if (io.w != w && cfg.motif) smear_from_last(cfg, st, io.w);  // (scan_tight.h tight_events_A)
                 if (io.w != w && cfg.s) st.xc.idx = io.w + (cfg.s >> 5) + 1;  // the cached plane word: the last b operand
                 w = io.w;
                 off = io.off;

@@ -453,6 +453,22 @@ RB_HD uint32_t smear_step(const LaneCfg& cfg, LaneState& st, uint32_t S, uint32_
 // same word is less than 32 positions back: below the cutoff. Otherwise the start is lastS and the component is kept iff
 // p0 + i - lastS - 1 >= cut, i.e. i >= lastS + cut + 1 - p0 (merge_core.h entry_interval computes the same interval).
 // cut1 = cut + 1.
+// bits thr..31 (all for thr <= 0, none for thr >= 32)
+RB_HD uint32_t bits_from(int thr) {
+    thr = thr < 0 ? 0 : thr;
+#ifdef __CUDA_ARCH__
+    return __funnelshift_lc(0u, 0xFFFFFFFFu, thr);  // the shift clamps at 32
+#else
+    return thr >= 32 ? 0u : (0xFFFFFFFFu << thr);
+#endif
+}
+// The general form, for any cutoff: `near` = the positions that have an S bit of THIS word at most cut positions below
+// them (in-word smear of S, by the caller). With an S bit below i in the word the component started there and is kept iff
+// i is not near; with none it started at lastS.
+RB_HD uint32_t keep_by_last_near(uint32_t E, uint32_t S, uint32_t near, int lastS, int cut1, int p0) {
+    const uint32_t upto = S ^ (S - 1u);  // bits up to and including the lowest S bit (all bits when the word has none)
+    return E & ~near & (~upto | bits_from(lastS + cut1 - p0));
+}
 RB_HD uint32_t keep_by_last(uint32_t E, uint32_t S, int lastS, int cut1, int p0) {
     const uint32_t below = S ^ (S - 1u);  // bits up to and including the lowest S bit of the word (all bits when it has none):
                                           // an S bit AT i starts the next component, it is not in front of i

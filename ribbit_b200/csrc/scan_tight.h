@@ -24,8 +24,9 @@ struct TightCfg {
     int exactA;          // the bit-parallel anchored keep filter is exact for this lane (cutA <= SMEAR_MAX; LARGE items: always)
     uint32_t amask;      // ~0 for lanes that own a shift, 0 for idle lanes (their anchors must read as 0)
     uint32_t mmask;      // ~0 for motif lanes
-    int d0, d1, d2, d3;  // smear shifts of the anchored keep filter, levels 0-3 (SMALL items; else 1, 2, 4, 8)
-    int d4, d5, d6;      //   levels 4-6 (LARGE items: d4 = anchored cutoff + 1, the others unused: keep_by_last)
+    int d0, d1, d2, d3;  // anchored keep filter: shifts that smear an S bit over the min(cutoff, 31) positions above it
+    int d4;              //   inside its word, levels 0-3 (SMALL items; MID: 1, 2, 4, 8) and 4 (LARGE: unused)
+    int cut1;            // anchored cutoff + 1
     int e0, e1, e2, e3, e4;  // doubling shifts of "K2 ones in a row" (SMALL items)
 };
 
@@ -43,12 +44,22 @@ struct TightState {
 RB_HD TightCfg make_tight_cfg(const LaneCfg& c, bool large = false) {  // large: the item runs tight_run<.., TIER_LARGE>
     TightCfg t;
     t.s = c.s; t.sh = c.s & 31; t.K2 = 2 * c.s;
-    t.exactA = c.cutA <= SMEAR_MAX;
+    t.exactA = 1;  // the tight loop's anchored keep filter is exact for every cutoff (tight_events_A)
     t.amask = c.s ? 0xFFFFFFFFu : 0u;
     t.mmask = c.motif ? 0xFFFFFFFFu : 0u;
-    t.d0 = (int)(c.dA & 63u); t.d1 = (int)((c.dA >> 6) & 63u); t.d2 = (int)((c.dA >> 12) & 63u); t.d3 = (int)((c.dA >> 18) & 63u);
-    t.d4 = (int)((c.dA >> 24) & 63u); t.d5 = (int)(c.dA2 & 63u); t.d6 = (int)((c.dA2 >> 6) & 63u);
-    if (large) { t.d4 = c.cutA + 1; t.exactA = 1; }
+    {
+        const int n = c.cutA < 31 ? c.cutA : 31;
+        int reach = 1, d[5];
+        for (int i = 0; i < 5; ++i) {
+            int sh = n - reach < reach ? n - reach : reach;
+            sh = sh < 0 ? 0 : sh;
+            d[i] = sh;
+            reach += sh;
+        }
+        t.d0 = d[0]; t.d1 = d[1]; t.d2 = d[2]; t.d3 = d[3]; t.d4 = d[4];
+    }
+    t.cut1 = c.cutA + 1;
+    (void)large;
     // five doubling steps reach min(K2, 32) ones in a row
     int k = 1, e[5];
     for (int i = 0; i < 5; ++i) {
@@ -202,28 +213,22 @@ template <int TIER>
 RB_HD void tight_events_A(const TightCfg& c, TightState& t, int p0, uint32_t passA, TightOut& o) {
     uint32_t sA, eA, sAp;
     ev_step(passA, t.ea, sA, eA, sAp);
+    // The cutoff is decided from the latest S bit in front of each E bit (scan_core.h keep_by_last): exact for every
+    // cutoff, and the loop carries no smear state (t.sm is not maintained: smear_from_last when the loop is left).
     if (TIER == TIER_LARGE) {
-        // every motif size of a LARGE item is at least 50: anchored cutoffs of 45 and more, decided from the position of
-        // the latest S bit (exact for every cutoff; t.sm is not maintained: smear_from_last when the loop is left)
-        o.x = keep_by_last(eA, sA, t.ea.lastS, c.d4, p0);
-        o.e = eA; o.s = sA; o.last = t.ea.lastS;
-        t.ea.lastS = sA ? p0 + 31 - clz32(sA) : t.ea.lastS;
-        return;
+        // every motif size of a LARGE item is at least 50: anchored cutoffs of 45 and more, an S bit in the same word is
+        // always too close
+        o.x = keep_by_last(eA, sA, t.ea.lastS, c.cut1, p0);
+    } else {
+        uint32_t near = sA << 1;
+        if (TIER == TIER_SMALL) { near |= near << c.d0; near |= near << c.d1; near |= near << c.d2; near |= near << c.d3; }
+        else { near |= near << 1; near |= near << 2; near |= near << 4; near |= near << 8; }  // (MID: every cutoff is at least 16)
+        near |= near << c.d4;
+        o.x = keep_by_last_near(eA, sA, near, t.ea.lastS, c.cut1, p0);
     }
-    uint32_t v = fsl(sAp, sA, 1);
-#define RB_TSMEAR(i, d)                                  \
-    {                                                    \
-        const uint32_t nv = v | fslc(t.sm[i], v, (d));  \
-        t.sm[i] = v;                                     \
-        v = nv;                                          \
-    }
-    // every motif size of a MID / LARGE item has a cutoff of at least 16: the first four levels are plain doublings
-    if (TIER == TIER_SMALL) { RB_TSMEAR(0, c.d0) RB_TSMEAR(1, c.d1) RB_TSMEAR(2, c.d2) RB_TSMEAR(3, c.d3) }
-    else { RB_TSMEAR(0, 1) RB_TSMEAR(1, 2) RB_TSMEAR(2, 4) RB_TSMEAR(3, 8) }  // (MID: every cutoff is at least 16)
-    RB_TSMEAR(4, c.d4) RB_TSMEAR(5, c.d5) RB_TSMEAR(6, c.d6)
-#undef RB_TSMEAR
-    o.x = eA & ~v; o.e = eA; o.s = sA; o.last = t.ea.lastS;
+    o.e = eA; o.s = sA; o.last = t.ea.lastS;
     t.ea.lastS = sA ? p0 + 31 - clz32(sA) : t.ea.lastS;
+    (void)sAp;
 }
 RB_HD void tight_events_S(TightState& t, int p0, uint32_t passS, TightOut& o) {
     uint32_t sS, eS, sSp;

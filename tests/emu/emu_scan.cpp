@@ -136,7 +136,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
     for (int j = 0; j < bw; ++j) {
         if (TIER != TIER_SMALL && tc[j].s && !prev_rare) ts[j].lenL = tight_lenL_lookup(tc[j], ts[j], cw, w);
         tight_leave(ts[j], st[j]);
-        if (TIER == TIER_LARGE && w != w_in && cfg[j].motif) smear_from_last(cfg[j], st[j], w);
+        if (w != w_in && cfg[j].motif) smear_from_last(cfg[j], st[j], w);
         if (w != w_in && cfg[j].s) st[j].xc.idx = w + (cfg[j].s >> 5) + 1;
     }
     return steps;
@@ -146,7 +146,9 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
 
 extern "C" {
 
-// Property check of the large-shift keep filter (scan_core.h keep_by_last, smear_from_last) on random event words:
+// Property check of the tight loop's keep filter (scan_core.h keep_by_last / keep_by_last_near, smear_from_last) on random
+// event words:
+//  (0) keep_by_last_near with the in-word smear of make_tight_cfg == kept_exact for every motif size 2..1000;
 //  (1) keep_by_last == kept_exact for every cutoff >= 32;
 //  (2) a lane that goes back to the smear network with the state smear_from_last builds gets the answers the network
 //      gives when it ran all along (cutoffs <= SMEAR_MAX).
@@ -156,6 +158,20 @@ int emu_keep_filter_check(uint64_t seed, int rounds) {
     auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
     auto sparse = [&](int k) { uint32_t v = 0xFFFFFFFFu; for (int i = 0; i < k; ++i) v &= (uint32_t)rnd(); return v; };
     int bad = 0;
+    for (int r = 0; r < rounds; ++r) {
+        const int m = 2 + (int)(rnd() % 999);
+        const LaneCfg cfg = make_lane_cfg(m, 2, 1000, 1, 1002, 2, 1000);
+        const TightCfg tc = make_tight_cfg(cfg);
+        if (cfg.cutA >= 16 && (tc.d0 != 1 || tc.d1 != 2 || tc.d2 != 4 || tc.d3 != 8)) ++bad;  // what the MID loop hard-codes
+        int lastS = -1;
+        for (int w = 0; w < 24; ++w) {
+            const uint32_t S = w ? sparse(2 + (int)(rnd() % 4)) : 1u, E = w ? sparse(1 + (int)(rnd() % 4)) : 0u;
+            uint32_t near = S << 1;
+            near |= near << tc.d0; near |= near << tc.d1; near |= near << tc.d2; near |= near << tc.d3; near |= near << tc.d4;
+            if (keep_by_last_near(E, S, near, lastS, tc.cut1, 32 * w) != kept_exact(cfg.cutA, 32 * w, E, S, lastS)) ++bad;
+            if (S) lastS = 32 * w + 31 - clz32(S);
+        }
+    }
     for (int r = 0; r < rounds; ++r) {
         const int m = 36 + (int)(rnd() % 965);  // cut_anch(m) >= 32
         const LaneCfg cfg = make_lane_cfg(m, 2, 1000, 1, 1002, 2, 1000);
