@@ -272,9 +272,8 @@ __device__ __forceinline__ void tight_step(TightLoop& q, const TightState& in, T
     const bool anyPS = __any_sync(FULL, (cand | passS) != 0u);
     const bool runS = anyPS || q.zc < 2;
     if (runS) {
-        const bool actS = __any_sync(FULL, passS != 0u);
         tight_events_S(t, p0, passS, os);
-        q.zc = actS ? 0 : q.zc + 1;
+        q.zc = anyPS ? 0 : q.zc + 1;  // (a perfect-run candidate counts as activity too: one vote instead of two)
     }
     // survivors of the prefilters that are not decided yet: exact check, bit by bit (rare)
     // (substitution stream: the prefilter is the cutoff itself while that is 10, i.e. for motif sizes up to 30)
@@ -357,7 +356,7 @@ __device__ __noinline__ void tight_run(TightIO* io) {
     q.flags = TF_SUSC | TF_SUSP | TF_PREV_RARE;
     q.lt = io->lt;
     q.o = __ldg(q.po); q.bb = __ldg(q.pb);
-    q.zc = 0;                      // consecutive words without a passing substitution window in any lane (saturating)
+    q.zc = 0;                      // consecutive words without a passing substitution window or perfect-run candidate in any lane (saturating)
     TightState ta = io->t, tb;
     // two words per trip with the roles of the two state objects swapped: the carried words of a step are born in other
     // registers than the ones they replace, so no register moves are needed at the loop end

@@ -103,12 +103,10 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
         for (int j = 0; j < bw; ++j) pair[j] = a[j] | a[j + 1 < bw ? j + 1 : j];
         uint32_t passS[32], passA[32], cand[32];
         TightOut oa[32], os[32];
-        bool actS = false;
         for (int j = 0; j < bw; ++j) {
             const uint32_t an = pair[j >= 2 ? j - 2 : j] | pair[j + 1 < bw ? j + 1 : j];
             tight_windows<TIER>(tc[j], ts[j], an, l1[j], passS[j], passA[j], cand[j]);
             tight_events_A<TIER>(tc[j], ts[j], 32 * w, passA[j], oa[j]);
-            actS |= passS[j] != 0u;
         }
         bool anyPS = false;
         for (int j = 0; j < bw; ++j) { cand[j] &= tc[j].mmask; anyPS |= (cand[j] | passS[j]) != 0u; }
@@ -121,7 +119,7 @@ long run_tight(const BandLayout& lay, const LaneCfg* cfg, LaneState* st, const P
             if (tc[j].s > 30 && os[j].x) os[j].x = kept_exact(cut_subst(tc[j].s), 32 * w, os[j].x, os[j].s, os[j].last);
             if (cand[j]) cand[j] = kept_exact_perfect(cw, w, tc[j].s, cut_perfect(tc[j].s), ts[j].xc, ts[j].xc & ~l1[j], cand[j]);
         }
-        if (runS) zc = actS ? 0 : zc + 1;
+        if (runS) zc = anyPS ? 0 : zc + 1;
         const uint32_t off = (uint32_t)io.raw.size();
         uint32_t elA = 0u, elS = 0u;
         for (int j = 0; j < bw; ++j) if (oa[j].x) io.raw.push_back(make_entry(STREAM_A, tc[j].s, oa[j].x, oa[j].s, oa[j].last));
