@@ -142,3 +142,38 @@ def test_keep_filter_of_the_large_shift_loop():
     L.emu_keep_filter_check.argtypes = [ctypes.c_uint64, ctypes.c_int]
     for seed in (1, 2, 3):
         assert L.emu_keep_filter_check(seed, 4000) == 0
+
+
+def _kept_digest(rows, off, lo=None, hi=None):
+    from ribbit_b200 import workloads as wl
+    k = (rows[:, 3] & 3) == 0  # neither DROPPED nor PSEUDO
+    return wl.digest_rows(rows[k, 0].astype(np.int64) + off, rows[k, 1].astype(np.int64) + off, rows[k, 2], lo, hi)
+
+
+def test_emulator_and_oracle_equal_the_reference_digests_of_the_bench_workload():
+    """The digests bench.py gates on (tests/golden/c3_digests.json, kept calls of the UNMODIFIED reference on the C3
+    workload): the kernels' logic on the CPU emulator reproduces them for the whole 47 Mbp contig and for the gate windows
+    of two more contigs (one over the end of the leading N run, one over the start of the 3 Mb N run); the oracle port
+    reproduces one window. Pins emulator, oracle and the gate's own digest code to the reference at bench scale."""
+    from ribbit_b200 import workloads as wl
+    g = wl.load_digests()
+    full = g["full"]["contig"]
+    seq = wl.c3_contig(full)
+    got, _ = emu_util.emu_streams(seq, 2, 100, chunk_words=8192)
+    for s in (1, 2, 3):
+        assert _kept_digest(got[s], 0) == g["full"]["kept"][str(s)], "contig %d stream %d" % (full, s)
+    for i in (19, 21):
+        seq = wl.c3_contig(i)
+        lo, hi = wl.c3_window(i, len(seq))
+        want = g["windows"][str(i)]
+        assert (want["L"], want["lo"], want["hi"]) == (len(seq), lo, hi)
+        got, _ = emu_util.emu_streams(seq[lo:hi], 2, 100, chunk_words=2048)
+        for s in (1, 2, 3):
+            assert _kept_digest(got[s], lo, lo, hi) == want["kept"][str(s)], "contig %d window stream %d" % (i, s)
+        if i == 21:
+            ev = ou.scan_events(seq[lo:hi], 2, 100)
+            for s in (1, 2, 3):
+                r = ev[ev[:, 0] == s]
+                k = wl.kept_mask(s, r[:, 1], r[:, 2], r[:, 3])
+                d = wl.digest_rows(r[k, 1].astype(np.int64) + lo, r[k, 2].astype(np.int64) + lo, r[k, 3], lo, hi)
+                assert d == want["kept"][str(s)], "oracle, contig %d window stream %d" % (i, s)
